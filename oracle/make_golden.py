@@ -1,0 +1,199 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE'S OWN FUNCTIONS.
+
+Run in the authoring container only (``python oracle/make_golden.py``): it imports
+MaxProjection.py, Illumination_QC_mult.py and Image_re-binning.py from /root/reference
+with ``boto3`` / ``imageio`` / ``tifffile`` replaced by in-memory stand-ins (those
+packages are not installed and carry no arithmetic), feeds them seeded inputs and stores
+inputs + outputs.  /root/reference does not exist on the GPU box, so the tests read only
+the committed fixtures.  Nothing from the reference is copied into this repository;
+the fixtures hold numbers, not code.
+"""
+import importlib.util
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+# ---- stand-ins for the I/O packages the reference imports at module top ------------
+class _Store(dict):
+    """Fake S3: keys -> bytes."""
+
+    def get_object(self, Bucket, Key):
+        return {"Body": io.BytesIO(self[(Bucket, Key)])}
+
+    def upload_fileobj(self, fileobj, bucket, key):
+        self[(bucket, key)] = fileobj.read()
+
+
+def _npy_bytes(a):
+    b = io.BytesIO()
+    np.save(b, a)
+    return b.getvalue()
+
+
+def _install_stubs():
+    boto3 = types.ModuleType("boto3")
+    boto3.client = lambda *a, **k: None
+    boto3.resource = lambda *a, **k: None
+    imageio = types.ModuleType("imageio")
+    imageio.imread = lambda f: np.load(io.BytesIO(f.read()))
+    imageio.imwrite = lambda f, arr, format=None: np.save(f, arr)
+    tifffile = types.ModuleType("tifffile")
+    tifffile.imread = lambda path: np.load(path)
+    tqdm = types.ModuleType("tqdm")
+    tqdm.tqdm = lambda it, **k: it
+    for name, mod in (("boto3", boto3), ("imageio", imageio), ("tifffile", tifffile)):
+        sys.modules.setdefault(name, mod)
+    try:
+        import tqdm as _t  # noqa: F401
+    except Exception:
+        sys.modules["tqdm"] = tqdm
+
+
+def _load(filename, modname):
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REF, filename))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def synth_plane(rng, h, w, lo=100, hi=4000, saturate=True):
+    a = rng.integers(lo, hi, (h, w), dtype=np.uint16)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for _ in range(6):
+        cy, cx = rng.integers(0, h), rng.integers(0, w)
+        r = rng.integers(4, 12)
+        blob = 20000.0 * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2.0 * r * r))
+        a = np.minimum(a.astype(np.float64) + blob, 65535).astype(np.uint16)
+    if saturate:
+        a[rng.integers(0, h, 5), rng.integers(0, w, 5)] = 65535
+    return a
+
+
+def smooth_illum(rng, h, w):
+    yy, xx = np.mgrid[0:h, 0:w]
+    r2 = ((yy - h / 2) / h) ** 2 + ((xx - w / 2) / w) ** 2
+    return (1.0 + 0.5 * (1.0 - r2 / r2.max()) + 0.01 * rng.random((h, w))).astype(np.float64)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    _install_stubs()
+    mp = _load("MaxProjection.py", "ref_maxproj")
+    qc = _load("Illumination_QC_mult.py", "ref_qc")
+    rb = _load("Image_re-binning.py", "ref_rebin")
+    rng = np.random.default_rng(20261018)
+
+    # ---- A1: MaxProjection.max_projection through its real signature ---------------
+    store = _Store()
+    cases = {}
+    for name, (z, h, w) in {"z3": (3, 48, 64), "z5": (5, 33, 47), "z1": (1, 16, 24)}.items():
+        planes = [synth_plane(rng, h, w) for _ in range(z)]
+        keys = [f"exp/Images/r01c01f01p{p:02d}-ch1.tiff" for p in range(z)]
+        for k, p in zip(keys, planes):
+            store[("bkt", k)] = _npy_bytes(p)
+        mp.max_projection(keys, "bkt", store)
+        out_key = mp.modify_imagepath(keys[0])
+        assert "ImagesStacked" in out_key
+        cases[f"{name}_in"] = np.stack(planes)
+        cases[f"{name}_out"] = np.load(io.BytesIO(store[("bkt", out_key)]))
+    try:
+        bad = [f"exp/Images/bad{p}.tiff" for p in range(2)]
+        store[("bkt", bad[0])] = _npy_bytes(np.zeros((4, 4), np.uint16))
+        store[("bkt", bad[1])] = _npy_bytes(np.zeros((4, 5), np.uint16))
+        mp.max_projection(bad, "bkt", store)
+        cases["mismatch_raises"] = np.array(0)
+    except ValueError:
+        cases["mismatch_raises"] = np.array(1)
+    cases["out_key"] = np.array(out_key)
+    np.savez_compressed(os.path.join(OUT, "maxproj.npz"), **cases)
+
+    # ---- A2 / A6 / A7: Illumination_QC_mult ------------------------------------------
+    cases = {}
+    tmp = "/tmp/ips_golden"
+    os.makedirs(tmp, exist_ok=True)
+    shapes = {"a": (96, 128), "b": (64, 64), "c": (40, 56), "small": (20, 30), "mid": (30, 36)}
+    for name, (h, w) in shapes.items():
+        img = synth_plane(rng, h, w)
+        ill = smooth_illum(rng, h, w)
+        path = os.path.join(tmp, f"{name}.npy")
+        np.save(path, img)
+        # process_site: (index, paths, channels, illum_cache) -> (index, dict)
+        idx, res = qc.process_site((7, [path, path, os.path.join(tmp, "missing.npy")],
+                                    ["chA", "chB", "chC"], [ill, None, None]))
+        assert idx == 7 and res["QC_Error_chC"] == "File Not Found"
+        corrected = img.astype(float) / ill
+        labels, magsum, powsum = qc.rps(corrected)
+        cases[f"{name}_img"] = img
+        cases[f"{name}_illum"] = ill
+        cases[f"{name}_rps_labels"] = np.asarray(labels)
+        cases[f"{name}_rps_mag"] = np.asarray(magsum, dtype=np.float64)
+        cases[f"{name}_rps_pow"] = np.asarray(powsum, dtype=np.float64)
+        cases[f"{name}_slope_corr"] = np.array(res["ImageQuality_PowerLogLogSlope_chA"], np.float64)
+        cases[f"{name}_pct_corr"] = np.array(res["ImageQuality_PercentMaximal_chA"], np.float64)
+        cases[f"{name}_slope_raw"] = np.array(res["ImageQuality_PowerLogLogSlope_chB"], np.float64)
+        cases[f"{name}_pct_raw"] = np.array(res["ImageQuality_PercentMaximal_chB"], np.float64)
+    # shape-mismatched illum is silently ignored (:149-153)
+    img = synth_plane(rng, 32, 40)
+    path = os.path.join(tmp, "mm.npy")
+    np.save(path, img)
+    _, res = qc.process_site((0, [path], ["x"], [np.ones((8, 8))]))
+    _, res_raw = qc.process_site((0, [path], ["x"], [None]))
+    assert res == res_raw
+    cases["mismatch_img"] = img
+    cases["mismatch_pct"] = np.array(res["ImageQuality_PercentMaximal_x"])
+    cases["mismatch_slope"] = np.array(res["ImageQuality_PowerLogLogSlope_x"])
+    const = np.full((48, 48), 1234.0)
+    m = qc.calculate_qc_metrics(const, "k")
+    cases["const_slope"] = np.array(m["ImageQuality_PowerLogLogSlope_k"])
+    cases["const_pct"] = np.array(m["ImageQuality_PercentMaximal_k"])
+    np.savez_compressed(os.path.join(OUT, "illum_qc.npz"), **cases)
+
+    # ---- A3: Image_re-binning.process_image_in_memory (TIFF bytes -> TIFF bytes) ------
+    from PIL import Image
+    cases = {}
+    for name, (h, w, oh, ow) in {"x2": (128, 128, 64, 64), "x4": (120, 160, 30, 40),
+                                 "odd": (90, 70, 41, 33), "full": (64, 96, 32, 48)}.items():
+        if name == "full":
+            img = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+            img[10:30, 20:50] = 65535          # plateau -> overshoot -> byte-clip quirk
+            img[40:50, 60:80] = 0
+        else:
+            img = synth_plane(rng, h, w)
+            img[5:15, 5:25] = 65535
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, format="tiff")
+        out_bytes = rb.process_image_in_memory(buf.getvalue(), target_size=(ow, oh))
+        out = np.asarray(Image.open(io.BytesIO(out_bytes)), dtype=np.uint16)
+        assert out.shape == (oh, ow)
+        cases[f"{name}_in"] = img
+        cases[f"{name}_out"] = out
+    np.savez_compressed(os.path.join(OUT, "rebin_lanczos.npz"), **cases)
+
+    # ---- A8: sklearn cosine_similarity as called by the reference ---------------------
+    from sklearn.metrics.pairwise import cosine_similarity
+    cases = {}
+    for name, (n, d) in {"g4": (4, 37), "g7": (7, 130), "g2": (2, 5), "g1": (1, 9)}.items():
+        x = rng.normal(size=(n, d))
+        if n > 2:
+            x[1] = 0.0                                     # zero row stays zero
+        s = cosine_similarity(x)
+        iu = np.triu_indices_from(s, k=1)
+        v = s[iu]
+        cases[f"{name}_x"] = x
+        cases[f"{name}_triu"] = v
+        cases[f"{name}_mean"] = np.array(np.mean(v) if len(v) > 0 else np.nan)
+    np.savez_compressed(os.path.join(OUT, "cosine.npz"), **cases)
+    print("golden fixtures written to", os.path.normpath(OUT))
+    for f in sorted(os.listdir(OUT)):
+        print(" ", f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
