@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the per-field hot path: fields/sec on 5-channel 2160^2 uint16 fields.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic fields: K1 (fused z-max ->
+illumination divide -> 2x2 sum bin) followed by K3 (per-object statistics over the Cellpose
+label mask), through the C-ABI of libips.so.  The workload is BASELINE.json configs[1]
+(one 384-well plate, 9 sites/well, 5ch 2160^2 uint16, 3 z-planes, ~2000 cells/site); with
+the defaults (216 steps x 16 fields) the timed region is exactly one 3456-field plate.
+
+Printed keys (one JSON line on rank 0): see the task contract.  ``value`` is device-resident
+throughput (inputs already in HBM), ``e2e`` is the same metric through the host-buffer
+pipeline (pinned host -> device copies and result read-back inside the timed region),
+``roofline`` is for the dominant kernel, ``cpu_baseline`` is the oracle (a NumPy/SciPy
+port of the reference's CPU path) on this box's host cores on a bounded sample.
+
+``--impl reference`` times that CPU path alone (no GPU work at all).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fields/sec (5ch 2160^2 uint16)"
+UNIT = "fields/s"
+C_, Z_, H_, W_, NCELLS, BIN = 5, 3, 2160, 2160, 2000, 2
+WORKLOAD = "configs[1]: 384-well plate x 9 sites, 5ch 2160x2160 uint16, 3 z-planes, ~2000 cells/site"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def k1_bytes_per_field(C, Z, H, W, b):
+    """raw read + illum read + max-proj write + binned fp32 write."""
+    return C * Z * H * W * 2 + C * H * W * 4 + C * H * W * 2 + C * (H // b) * (W // b) * 4
+
+
+def k3_bytes_per_field(C, H, W, n_cells):
+    """labels + max-proj + illum reads + object rows written."""
+    return H * W * 4 + C * H * W * 2 + C * H * W * 4 + n_cells * (6 + 2 + 5 * C) * 4
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic plate
+# ---------------------------------------------------------------------------------------
+def base_label_masks(n_base, h, w, n_cells, seed):
+    from image_processing_suite_b200 import synth
+    return [synth.make_labels(h, w, n_cells, seed=seed + 17 * k) for k in range(n_base)]
+
+
+def dihedral(lab, k):
+    """k in 0..7: the 8 symmetries of the square (keeps labels non-overlapping, 1..N)."""
+    a = np.rot90(lab, k % 4)
+    if k >= 4:
+        a = a[:, ::-1]
+    return np.ascontiguousarray(a)
+
+
+def ring_masks(n, h, w, n_cells, seed=0):
+    n_base = (n + 7) // 8
+    bases = base_label_masks(n_base, h, w, n_cells, seed)
+    return [dihedral(bases[i // 8], i % 8) for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------
+# clock sampling during the timed region
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index, period=0.02):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self.period = period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons - {"gpu_idle"}), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU path (oracle) -- the reference arm and the cpu_baseline leg
+# ---------------------------------------------------------------------------------------
+def cpu_field(raw, labels, illum, b, scale):
+    """The reference's CPU arithmetic for one field: np.maximum.reduce per channel
+    (MaxProjection.py:45), astype(float)/illum (Illumination_QC_mult.py:145-150), b x b sum
+    binning, scipy.ndimage labelled statistics (CellProfiler MeasureObject* restatement)."""
+    from oracle import object_stats as o_obj
+    from oracle import preprocess as o_pre
+    mp = np.stack([o_pre.max_projection(list(raw[c])) for c in range(raw.shape[0])])
+    corr = np.stack([o_pre.illum_correct(mp[c], illum[c]) for c in range(raw.shape[0])])
+    binned = o_pre.sum_bin(corr, b)
+    ints, flts = o_obj.object_stats(labels, mp, illum, scale)
+    return mp, binned, ints, flts
+
+
+def cpu_band(raw, labels, illum, rows):
+    return raw[:, :, :rows], labels[:rows], illum[:, :rows]
+
+
+def run_cpu_path(fields, illum, n_threads, b=BIN, scale=1.0 / 65535.0):
+    """Process a list of (raw, labels) with a thread pool, as Illumination_QC_mult.py:212 does."""
+    import concurrent.futures as cf
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=n_threads) as ex:
+        futs = [ex.submit(cpu_field, r, l, illum, b, scale) for r, l in fields]
+        for fu in futs:
+            fu.result()
+    return time.perf_counter() - t0
+
+
+def host_fields(n, h, w, seed=0):
+    from image_processing_suite_b200 import synth
+    masks = ring_masks(n, h, w, NCELLS if h == H_ else max(1, NCELLS * h * w // (H_ * W_)), seed)
+    return [(synth.field_numpy(m, c=C_, z=Z_, seed=seed + i), m) for i, m in enumerate(masks)]
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    reference is Python scripts around NumPy/SciPy calls and CellProfiler, nothing to
+    compile), all host threads, bounded sample per step."""
+    from image_processing_suite_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    illum = synth.make_illum(C_, H_, W_, seed=0).astype(np.float64)
+    # a few distinct fields, cycled; generation is outside the timed region
+    n_distinct = min(cores, 8)
+    fields = host_fields(n_distinct, H_, W_, seed=0)
+    # size one step: time one full field on one thread, then pick rows so that
+    # (warmup + steps) steps, each `cores` band-fields wide, fit the budget
+    t1 = run_cpu_path(fields[:1], illum, 1)
+    budget_s = float(args.ref_budget)
+    per_step_budget = budget_s / max(args.steps + args.warmup, 1)
+    # with `cores` threads a step of `cores` fields takes ~t1 * contention; assume 1.5x
+    frac = min(1.0, per_step_budget / (t1 * 1.5))
+    rows = max(8, int(H_ * frac) // 4 * 4)
+    per_step = cores
+    step_fields = [cpu_band(*fields[i % n_distinct], illum, rows) for i in range(per_step)]
+    step_in = [(r, l) for r, l, _ in step_fields]
+    ill_band = illum[:, :rows]
+    for _ in range(args.warmup):
+        run_cpu_path(step_in, ill_band, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += run_cpu_path(step_in, ill_band, cores)
+    field_equiv = per_step * rows / float(H_)
+    value = field_equiv * args.steps / t
+    sample = "%d threads x %d-row band of a 2160-row field per step (%.3f field-equivalents/step), %d distinct fields" % (
+        cores, rows, field_equiv, n_distinct)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "bin": BIN, "cpu_path": "numpy/scipy.ndimage oracle port"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_leg(host_ring, illum_host, budget_s=20.0):
+    """Bounded sample of the same workload on this box's cores (rank 0, N=1 only)."""
+    cores = os.cpu_count() or 1
+    illum64 = illum_host.astype(np.float64)
+    n = min(len(host_ring), cores, 16)
+    t1 = run_cpu_path(host_ring[:1], illum64, 1)
+    if t1 * 1.5 > budget_s:                      # very slow host: shrink to a band
+        rows = max(8, int(H_ * budget_s / (t1 * 1.5)) // 4 * 4)
+    else:
+        rows = H_
+    sample = [(r[:, :, :rows], l[:rows]) for r, l in host_ring[:n]]
+    t = run_cpu_path(sample, illum64[:, :rows], cores)
+    fe = n * rows / float(H_)
+    return {"value": fe / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d fields x %d rows of %d on %d threads (%.1f s); 1 field on 1 thread: %.2f s" % (
+                n, rows, H_, cores, t, t1)}
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    from image_processing_suite_b200 import capi, ops, synth
+    from image_processing_suite_b200.pipeline import FieldPipeline, pinned_empty
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    Fb, R = args.batch, args.ring
+    assert R % Fb == 0, "--ring must be a multiple of --batch"
+    # ---- synthetic plate shard: a ring of R distinct device-resident fields ---------------
+    masks = ring_masks(R, H_, W_, NCELLS, seed=1000 * rank)
+    labels = torch.empty((R, H_, W_), dtype=torch.int32, device=dev)
+    raw = torch.empty((R, C_, Z_, H_, W_), dtype=torch.uint16, device=dev)
+    for i, m in enumerate(masks):
+        labels[i].copy_(torch.from_numpy(m))
+        raw[i].copy_(synth.field_torch(labels[i], c=C_, z=Z_, seed=1000 * rank + i))
+    illum_host = synth.make_illum(C_, H_, W_, seed=0)
+    illum = torch.from_numpy(illum_host).to(dev)
+    n_max = NCELLS
+    scale = 1.0 / 65535.0
+
+    nb = R // Fb
+    k1_out = [None] * nb
+    k3_out = [None] * nb
+    for b in range(nb):                                   # preallocate every output once
+        k1_out[b] = ops.preprocess_fused(raw[b * Fb:(b + 1) * Fb], illum, bin=BIN)
+        k3_out[b] = ops.object_stats(labels[b * Fb:(b + 1) * Fb], k1_out[b]["maxproj"], illum, scale, n_max=n_max)
+    torch.cuda.synchronize()
+
+    def step(i, ev=None):
+        b = i % nb
+        sl = slice(b * Fb, (b + 1) * Fb)
+        if ev is not None:
+            ev[0].record()
+        ops.preprocess_fused(raw[sl], illum, bin=BIN, out=k1_out[b])
+        if ev is not None:
+            ev[1].record()
+        ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=k3_out[b])
+        if ev is not None:
+            ev[2].record()
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = capi.launch_count()
+    with ClockSampler(local) as clocks:
+        t_begin.record()
+        for i in range(args.steps):
+            step(args.warmup + i, evs[i])
+        t_end.record()
+        barrier()
+    launches = capi.launch_count() - l0
+    ms_total = t_begin.elapsed_time(t_end)
+    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    k3_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    fields_total = args.steps * Fb * world
+    value = fields_total / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer pipeline -------------------------------------
+    e2e = None
+    Fe = args.e2e_batch
+    n_host = args.e2e_ring
+    pipe = FieldPipeline(Fe, C_, Z_, H_, W_, bin=BIN, n_max=n_max, depth=3, illum=illum_host,
+                         intensity_scale=scale)
+    h_raw = [pinned_empty((Fe, C_, Z_, H_, W_), np.uint16) for _ in range(n_host)]
+    h_lab = [pinned_empty((Fe, H_, W_), np.int32) for _ in range(n_host)]
+    for j in range(n_host):
+        for k in range(Fe):
+            src = (j * Fe + k) % R
+            h_raw[j][k] = raw[src].cpu().numpy()
+            h_lab[j][k] = labels[src].cpu().numpy()
+    h_out = [pipe.output_buffers() for _ in range(3)]
+    e2e_steps = max(1, args.e2e_fields // Fe)
+    for i in range(3):
+        pipe.wait(pipe.submit(h_raw[i % n_host], h_lab[i % n_host], h_out[i % 3]))
+    barrier()
+    l1 = capi.launch_count()
+    t0 = time.perf_counter()
+    tickets = []
+    for i in range(e2e_steps):
+        if i >= 3:
+            pipe.wait(tickets[i - 3])                     # its host output buffers are about to be reused
+        tickets.append(pipe.submit(h_raw[i % n_host], h_lab[i % n_host], h_out[i % 3]))
+    for tk in tickets[-3:]:
+        pipe.wait(tk)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = capi.launch_count() - l1
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": e2e_steps * Fe * world / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes(h_out[0]),
+           "fields_per_step": Fe, "steps": e2e_steps, "timer": "host wall clock around submit..wait (copies + kernels)",
+           "gpu_launches": e2e_launches}
+    n_obj_last = h_out[(e2e_steps - 1) % 3]["n_objects"].copy()
+    pipe.close()
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ring = [(h_raw[j][k], h_lab[j][k]) for j in range(n_host) for k in range(Fe)]
+        cpu = cpu_baseline_leg(ring, illum_host, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        kb1 = k1_bytes_per_field(C_, Z_, H_, W_, BIN) * Fb
+        kb3 = k3_bytes_per_field(C_, H_, W_, NCELLS) * Fb
+        g1 = kb1 / (k1_ms * 1e-3) / 1e9
+        g3 = kb3 / (k3_ms * 1e-3) / 1e9
+        dominant = "K1 preprocess_vec_kernel" if k1_ms >= k3_ms else "K3 object_stats_scan_kernel(+init+compact)"
+        ga = g1 if k1_ms >= k3_ms else g3
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get("K1" if k1_ms >= k3_ms else "K3")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u16 in / f32 + f64 accumulate",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "fields_per_step": Fb, "bin": BIN, "n_cells": NCELLS,
+                       "ring_fields": R, "l2": "inputs larger than L2: ring of %d distinct fields = %.1f GB" % (
+                           R, R * (C_ * Z_ * H_ * W_ * 2 + H_ * W_ * 4) / 1e9),
+                       "sharding": "fields by well across ranks, no data-path collective"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ga, "peak": peak, "unit": "GB/s",
+                         "frac": ga / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kb1 if k1_ms >= k3_ms else kb3},
+            "kernels": {"K1": {"ms_per_launch": k1_ms, "gbs": g1, "frac": g1 / peak, "bytes_per_field": kb1 // Fb},
+                        "K3": {"ms_per_launch": k3_ms, "gbs": g3, "frac": g3 / peak, "bytes_per_field": kb3 // Fb}},
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+            "objects_last_field": int(n_obj_last[-1]),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=216)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="fields per step")
+    ap.add_argument("--ring", type=int, default=32, help="distinct device-resident fields")
+    ap.add_argument("--e2e-batch", type=int, default=4)
+    ap.add_argument("--e2e-ring", type=int, default=4, help="distinct pinned host batches")
+    ap.add_argument("--e2e-fields", type=int, default=256)
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--ref-budget", type=float, default=120.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,155 @@
+"""Tensor-level entry points: torch tensors in, torch tensors out, arithmetic in libips.so.
+
+PyTorch is used for device memory and streams only; every function below validates its
+arguments, allocates outputs / workspace with torch and calls one C-ABI entry point on
+the current CUDA stream.  Nothing here computes on the CPU and nothing imports oracle/.
+"""
+import ctypes as C
+
+import torch
+
+from . import capi
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _check(t, name, dtype, ndim=None, dev=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s (got %s)" % (name, dtype, t.dtype))
+    if not t.is_cuda:
+        raise ValueError("%s must live on a CUDA device (there is no CPU path)" % name)
+    if dev is not None and t.device != dev:
+        raise ValueError("%s is on %s, expected %s" % (name, t.device, dev))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dimensions (got %s)" % (name, ndim, tuple(t.shape)))
+    return t
+
+
+def _workspace(nbytes, dev):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+
+def device_info():
+    sm, ma, mi, l2 = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    capi.call("ips_device_info", C.byref(sm), C.byref(ma), C.byref(mi), C.byref(l2))
+    return {"sm_count": sm.value, "cc": (ma.value, mi.value), "l2_bytes": l2.value}
+
+
+# ---- K1 ---------------------------------------------------------------------------------
+def preprocess_fused(raw, illum=None, bin=1, want_maxproj=True, want_corrected=False,
+                     want_binned=True, want_pct_maximal=False, out=None):
+    """Fused z-max -> illumination divide -> bin x bin sum (K1).
+
+    raw [F][C][Z][H][W] uint16 (device); illum [C][H][W] float32 or None.
+    Returns a dict with the requested outputs: ``maxproj`` uint16 [F][C][H][W],
+    ``corrected`` float32 [F][C][H][W], ``binned`` [F][C][H/bin][W/bin] (uint32 sums
+    stored as int32-viewable ``torch.uint32`` when illum is None, float32 otherwise),
+    ``pct_maximal`` float64 [F][C].  ``out`` may carry preallocated tensors under the
+    same keys (reused by the benchmark ring).
+    Replaces MaxProjection.py:45, Illumination_QC_mult.py:145-150 and :73-95.
+    """
+    _check(raw, "raw", torch.uint16, 5)
+    dev = raw.device
+    F, Cn, Z, H, W = raw.shape
+    if illum is not None:
+        _check(illum, "illum", torch.float32, 3, dev)
+        if tuple(illum.shape) != (Cn, H, W):
+            raise ValueError("illum shape %s does not match the field (%d, %d, %d)" %
+                             (tuple(illum.shape), Cn, H, W))
+    if bin not in (1, 2, 4):
+        raise ValueError("bin must be 1, 2 or 4")
+    if H % bin or W % bin:
+        raise ValueError("image size %dx%d is not divisible by bin %d" % (H, W, bin))
+    if want_corrected and illum is None:
+        raise ValueError("corrected output requires an illumination function")
+    out = dict(out or {})
+    res = {}
+    with torch.cuda.device(dev):
+        if want_maxproj:
+            res["maxproj"] = out.get("maxproj")
+            if res["maxproj"] is None:
+                res["maxproj"] = torch.empty((F, Cn, H, W), dtype=torch.uint16, device=dev)
+            _check(res["maxproj"], "out.maxproj", torch.uint16, 4, dev)
+        if want_corrected:
+            res["corrected"] = out.get("corrected")
+            if res["corrected"] is None:
+                res["corrected"] = torch.empty((F, Cn, H, W), dtype=torch.float32, device=dev)
+            _check(res["corrected"], "out.corrected", torch.float32, 4, dev)
+        if want_binned:
+            bdt = torch.float32 if illum is not None else torch.uint32
+            res["binned"] = out.get("binned")
+            if res["binned"] is None:
+                res["binned"] = torch.empty((F, Cn, H // bin, W // bin), dtype=bdt, device=dev)
+            _check(res["binned"], "out.binned", bdt, 4, dev)
+        ws, ws_bytes = None, 0
+        if want_pct_maximal:
+            res["pct_maximal"] = out.get("pct_maximal")
+            if res["pct_maximal"] is None:
+                res["pct_maximal"] = torch.empty((F, Cn), dtype=torch.float64, device=dev)
+            ws_bytes = capi.call("ips_preprocess_workspace_bytes", F, Cn, H, W, bin)
+            ws = out.get("ws")
+            if ws is None or ws.numel() < ws_bytes:
+                ws = _workspace(ws_bytes, dev)
+            res["ws"] = ws
+        if F > 0:
+            capi.call("ips_preprocess_fused", _ptr(raw), _ptr(illum), _ptr(res.get("maxproj")),
+                      _ptr(res.get("corrected")), _ptr(res.get("binned")), bin,
+                      _ptr(res.get("pct_maximal")), _ptr(ws), ws_bytes, F, Cn, Z, H, W, _stream(dev))
+    return res
+
+
+# ---- K3 ---------------------------------------------------------------------------------
+def object_stats(labels, maxproj, illum=None, intensity_scale=1.0, n_max=None, out=None):
+    """Per-object statistics over label masks (K3).
+
+    labels [F][H][W] int32, maxproj [F][C][H][W] uint16, illum [C][H][W] float32 or None.
+    Returns dict: ``n_objects`` int32 [F], ``ints`` int32 [F][Nmax][6] (label, area, y0,
+    x0, y1, x1), ``flts`` float32 [F][Nmax][2+5C] (cy, cx, then per channel sum, mean,
+    std, min, max).  Rows beyond n_objects[f] are unspecified.  ``n_max`` bounds the label
+    values (default: labels.max(), which costs a device sync).
+    Replaces the CellProfiler subprocess of Feature_extraction_opt.py:166-167.
+    """
+    _check(labels, "labels", torch.int32, 3)
+    dev = labels.device
+    F, H, W = labels.shape
+    _check(maxproj, "maxproj", torch.uint16, 4, dev)
+    if maxproj.shape[0] != F or tuple(maxproj.shape[2:]) != (H, W):
+        raise ValueError("maxproj shape %s does not match labels %s" % (tuple(maxproj.shape), tuple(labels.shape)))
+    Cn = maxproj.shape[1]
+    if illum is not None:
+        _check(illum, "illum", torch.float32, 3, dev)
+        if tuple(illum.shape) != (Cn, H, W):
+            raise ValueError("illum shape mismatch")
+    if n_max is None:
+        n_max = int(labels.max().item()) if labels.numel() else 0
+    n_max = max(int(n_max), 1)
+    out = dict(out or {})
+    with torch.cuda.device(dev):
+        n_obj = out.get("n_objects")
+        if n_obj is None:
+            n_obj = torch.empty((F,), dtype=torch.int32, device=dev)
+        ints = out.get("ints")
+        if ints is None:
+            ints = torch.empty((F, n_max, 6), dtype=torch.int32, device=dev)
+        flts = out.get("flts")
+        if flts is None:
+            flts = torch.empty((F, n_max, 2 + 5 * Cn), dtype=torch.float32, device=dev)
+        ws_bytes = capi.call("ips_object_stats_workspace_bytes", F, Cn, n_max)
+        ws = out.get("ws")
+        if ws is None or ws.numel() < ws_bytes:
+            ws = _workspace(ws_bytes, dev)
+        if F > 0:
+            capi.call("ips_object_stats", _ptr(labels), _ptr(maxproj), _ptr(illum), float(intensity_scale),
+                      _ptr(n_obj), _ptr(ints), _ptr(flts), n_max, _ptr(ws), ws.numel(), F, Cn, H, W,
+                      _stream(dev))
+    return {"n_objects": n_obj, "ints": ints, "flts": flts, "ws": ws}

@@ -1,0 +1,187 @@
+/*
+ * ips.h -- C ABI of the B200-native hot path of the image-processing suite.
+ *
+ * The reference (Saguaro-Biosciences/image-processing-suite) has no FFI: its boundary is
+ * "Python function inside a CLI script".  Each entry point below replaces the arithmetic
+ * of one such function; the reference site is cited as file:line relative to the
+ * reference repository.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add at each site.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no exceptions across the boundary;
+ *   - return 0 (IPS_OK) or a negative IPS_ERR_* code; ips_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread;
+ *   - device pointers unless the name says _host; row-major, contiguous; base pointers
+ *     16-byte aligned; never allocate or free caller-visible memory (scratch comes in
+ *     through (ws, ws_bytes), sized by the matching *_workspace_bytes query);
+ *   - asynchronous on the cudaStream_t passed as `stream` (typed void* so that C callers
+ *     do not need cuda_runtime.h); re-entrant and thread-safe across distinct streams.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with IPS_ERR_CUDA.
+ */
+#ifndef IPS_H_
+#define IPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPS_ABI_VERSION 1
+
+enum {
+  IPS_OK = 0,
+  IPS_ERR_BAD_SHAPE = -1,
+  IPS_ERR_BAD_DTYPE = -2,
+  IPS_ERR_BAD_ALIGN = -3,
+  IPS_ERR_CUDA = -4,
+  IPS_ERR_NCCL = -5,
+  IPS_ERR_NOMEM = -6,
+  IPS_ERR_BAD_ARG = -7
+};
+
+typedef void* ips_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------- */
+int ips_abi_version(void);
+const char* ips_last_error(void);
+/* Number of kernel launches this library has issued from the calling process so far
+ * (bench.py reports the difference across its timed region as "gpu_launches"). */
+uint64_t ips_launch_count(void);
+/* sm_count, compute capability and L2 size of the current device. */
+int ips_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+
+/* ---- K1: fused z-max -> illumination divide -> b x b sum-bin ---------------------
+ * Replaces  np.maximum.reduce(images)                 MaxProjection.py:45
+ *           img.astype(float) / illum_cache[i]        Illumination_QC_mult.py:145-150,
+ *                                                      Cellpose_GPU_s3fs.py:72
+ *           calculate_saturation_cp_exact (optional)  Illumination_QC_mult.py:73-95
+ *           and north_star's 2x2 / 4x4 sum re-binning (no reference site).
+ *
+ * raw        [F][C][Z][H][W] uint16
+ * illum      [C][H][W] float32, or NULL (no correction)
+ * maxproj    [F][C][H][W] uint16, or NULL
+ * corrected  [F][C][H][W] float32 = maxproj / illum, or NULL (requires illum)
+ * binned     [F][C][H/bin][W/bin]: uint32 sums of maxproj when illum == NULL, float32
+ *            sums of corrected otherwise; or NULL.  bin in {1, 2, 4}; H, W % bin == 0.
+ * pct_maximal[F][C] float64 = 100 * #(x == max x) / (H*W) evaluated on the float64
+ *            quotient (or on the integer max projection when illum == NULL), or NULL.
+ *            Needs ws of ips_preprocess_workspace_bytes(); ws may be NULL otherwise.
+ */
+size_t ips_preprocess_workspace_bytes(int F, int C, int H, int W, int bin);
+int ips_preprocess_fused(const uint16_t* raw, const float* illum, uint16_t* maxproj,
+                         float* corrected, void* binned, int bin, double* pct_maximal,
+                         void* ws, size_t ws_bytes, int F, int C, int Z, int H, int W,
+                         ips_stream_t stream);
+
+/* ---- K3: per-object statistics over a label mask -----------------------------------
+ * Replaces the CellProfiler 4.2.8 MeasureObjectSizeShape / MeasureObjectIntensity
+ * subprocess launched at Feature_extraction_opt.py:166-167 (schema consumers
+ * Normalize_CP_ami.py:47-127, Pycyto_pertime.py:46-75) and the regionprops loop of
+ * Cellpose_GPU_s3fs.py:149-170 (label / bbox / centroid conventions).
+ *
+ * labels     [F][H][W] int32, 0 = background, objects 1..Nmax
+ * maxproj    [F][C][H][W] uint16;  illum [C][H][W] float32 or NULL
+ * intensity value of a pixel = maxproj / illum * intensity_scale
+ * n_objects  [F] int32: number of rows written for the field, or -1 if a label > Nmax
+ *            was met (rows of that field are then unspecified)
+ * ints       [F][Nmax][6] int32: label, area, y0, x0, y1, x1 (half-open box)
+ * flts       [F][Nmax][2+5C] float32: centroid y, x; per channel sum, mean,
+ *            population std, min, max.  Rows are in ascending label order, absent
+ *            labels are skipped (regionprops convention).  1 <= C <= 8.
+ */
+size_t ips_object_stats_workspace_bytes(int F, int C, int Nmax);
+int ips_object_stats(const int32_t* labels, const uint16_t* maxproj, const float* illum,
+                     float intensity_scale, int32_t* n_objects, int32_t* ints, float* flts,
+                     int Nmax, void* ws, size_t ws_bytes, int F, int C, int H, int W,
+                     ips_stream_t stream);
+
+/* ---- K2: per-plate illumination-function estimation ----------------------------------
+ * Produces the {ch}_illum.npy functions that Illumination_QC_mult.py:186-193 and
+ * Cellpose_GPU_s3fs.py:56 load (the reference computes them outside the repository).
+ * accumulate: acc[c][y][x] += sum_f maxproj[f][c][y][x]   (uint32, exact up to 65537 fields)
+ * finalize:   mean = acc / n_fields; edge-normalised separable Gaussian (sigma, truncate
+ *             4.0); divide by the robust minimum (sorted positive values at position
+ *             int(n * robust_frac)) and clamp below at 1.
+ */
+int ips_illum_accumulate(const uint16_t* maxproj, uint32_t* acc, int F, int C, int H, int W,
+                         ips_stream_t stream);
+size_t ips_illum_finalize_workspace_bytes(int C, int H, int W);
+int ips_illum_finalize(const uint32_t* acc, uint64_t n_fields, float sigma, float robust_frac,
+                       float* illum_out, void* ws, size_t ws_bytes, int C, int H, int W,
+                       ips_stream_t stream);
+/* Per-pixel median over a device-resident stack (median mode): stack [N][C][H][W] uint16
+ * -> raw_out [C][H][W] float32 (mean of the two middle values for even N). */
+int ips_illum_median(const uint16_t* stack, float* raw_out, int N, int C, int H, int W,
+                     ips_stream_t stream);
+/* Gaussian + robust rescale on a float32 raw function (shared by mean and median mode). */
+int ips_illum_smooth_rescale(const float* raw, float sigma, float robust_frac, float* illum_out,
+                             void* ws, size_t ws_bytes, int C, int H, int W, ips_stream_t stream);
+
+/* ---- K5: Pillow-exact LANCZOS resize of 16-bit planes -------------------------------
+ * Replaces  img.resize(target_size, resample=LANCZOS)   Image_re-binning.py:18
+ * in  [C][H][W] uint16 -> out [C][outH][outW] uint16, bit-exact with Pillow 12.2.0's
+ * I;16 path (horizontal pass, round, vertical pass; double accumulation; per-byte clip).
+ */
+size_t ips_lanczos_workspace_bytes(int C, int H, int W, int outH, int outW);
+int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, int H, int W, int outH,
+                           int outW, void* ws, size_t ws_bytes, ips_stream_t stream);
+
+/* ---- K6: radial power spectrum ring sums ----------------------------------------------
+ * Replaces the ring binning of rps()   Illumination_QC_mult.py:39-43, :61-68
+ * spec [F][H][W] complex64/complex128-free interface: re/im planes are passed as an
+ * interleaved float64 array [F][H][W][2] (the unshifted 2-D DFT of the mean-removed
+ * image).  mag_out / pow_out [F][n_rings] float64 for ring labels 2 .. n_rings+1.
+ */
+int ips_ring_sums(const double* spec_interleaved, double* mag_out, double* pow_out, int n_rings,
+                  int F, int H, int W, ips_stream_t stream);
+
+/* ---- K4: replicate-group cosine similarity, strict upper triangle ---------------------
+ * Replaces  cosine_similarity(features) -> triu(k=1) -> mean
+ *           Feature_select_cosine_ami.py:145-149, Pycyto_pertime.py:132-140
+ * X [N][D] float32 (NaN already replaced by 0).  Rows are L2-normalised (zero rows stay
+ * zero).  group [N] int32 (rows of one group must be contiguous) or NULL (one group).
+ * sum_out[g] float64 = sum over i<j in group g of cos(i, j); npairs_out[g] = #pairs.
+ */
+size_t ips_cosine_workspace_bytes(int N, int D);
+int ips_cosine_triu(const float* X, const int32_t* group, int n_groups, double* sum_out,
+                    uint64_t* npairs_out, int N, int D, void* ws, size_t ws_bytes,
+                    ips_stream_t stream);
+
+/* ---- well-level aggregation (consumer of the all-gather) -------------------------------
+ * Replaces  df.groupby("Metadata_Well").agg("mean")    Normalize_CP_ami.py:126,
+ *                                                       Pycyto_pertime.py:69-72
+ * rows [N][D] float32, well [N] int32 in [0, n_wells) -> mean_out [n_wells][D] float64,
+ * count_out [n_wells] int32 (wells without rows get NaN means, as an absent group).
+ */
+size_t ips_well_mean_workspace_bytes(int n_wells, int D);
+int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
+                  int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream);
+
+/* ---- host-buffer pipeline (the end-to-end call a script makes) -------------------------
+ * One call = H2D of a batch of raw fields + label masks, K1, K3, D2H of max projections,
+ * binned planes and object rows, on three streams with `depth` device slots so that
+ * copies and kernels of consecutive batches overlap.  Host buffers must be page-locked
+ * (ips_host_alloc) for the copies to be asynchronous.
+ */
+typedef struct ips_pipeline ips_pipeline_t;
+int ips_host_alloc(void** out, size_t bytes);
+int ips_host_free(void* p);
+int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, int C, int Z, int H, int W,
+                        int bin, int Nmax, int depth, const float* illum_host /* or NULL */,
+                        float intensity_scale);
+/* Enqueue one batch; returns a ticket (>= 0) or a negative error.  Output pointers may be
+ * NULL to skip that device->host copy. */
+int64_t ips_pipeline_submit(ips_pipeline_t* p, const uint16_t* raw_host,
+                            const int32_t* labels_host, uint16_t* maxproj_host,
+                            void* binned_host, int32_t* n_objects_host, int32_t* ints_host,
+                            float* flts_host);
+int ips_pipeline_wait(ips_pipeline_t* p, int64_t ticket); /* blocks until that batch's outputs landed */
+int ips_pipeline_destroy(ips_pipeline_t* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPS_H_ */
