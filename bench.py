@@ -269,11 +269,16 @@ def gpu_arm(args):
     scale = 1.0 / 65535.0
 
     nb = R // Fb
+    fused = args.mode == "fused"
     k1_out = [None] * nb
     k3_out = [None] * nb
     for b in range(nb):                                   # preallocate every output once
-        k1_out[b] = ops.preprocess_fused(raw[b * Fb:(b + 1) * Fb], illum, bin=BIN)
-        k3_out[b] = ops.object_stats(labels[b * Fb:(b + 1) * Fb], k1_out[b]["maxproj"], illum, scale, n_max=n_max)
+        sl = slice(b * Fb, (b + 1) * Fb)
+        if fused:
+            k1_out[b] = ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max)
+        else:
+            k1_out[b] = ops.preprocess_fused(raw[sl], illum, bin=BIN)
+            k3_out[b] = ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max)
     torch.cuda.synchronize()
 
     def step(i, ev=None):
@@ -281,6 +286,12 @@ def gpu_arm(args):
         sl = slice(b * Fb, (b + 1) * Fb)
         if ev is not None:
             ev[0].record()
+        if fused:
+            ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max, out=k1_out[b])
+            if ev is not None:
+                ev[1].record()
+                ev[2].record()
+            return
         ops.preprocess_fused(raw[sl], illum, bin=BIN, out=k1_out[b])
         if ev is not None:
             ev[1].record()
@@ -367,18 +378,36 @@ def gpu_arm(args):
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        kb1 = k1_bytes_per_field(C_, Z_, H_, W_, BIN) * Fb
-        kb3 = k3_bytes_per_field(C_, H_, W_, NCELLS) * Fb
-        g1 = kb1 / (k1_ms * 1e-3) / 1e9
-        g3 = kb3 / (k3_ms * 1e-3) / 1e9
-        dominant = "K1 preprocess_vec_kernel" if k1_ms >= k3_ms else "K3 object_stats_scan_kernel(+init+compact)"
-        ga = g1 if k1_ms >= k3_ms else g3
+        # Algorithmic bytes per LAUNCH (DESIGN.md "Roofline accounting"): every per-field
+        # stream once per field; the plate-constant illumination function once per launch
+        # (it is shared by the launch's fields and served from L2 after the first touch).
+        ill_b = C_ * H_ * W_ * 4
+        per_field = {
+            "K1": k1_bytes_per_field(C_, Z_, H_, W_, BIN) - ill_b,
+            "K3": k3_bytes_per_field(C_, H_, W_, NCELLS) - ill_b,
+        }
+        per_field["fused"] = per_field["K1"] + H_ * W_ * 4 + NCELLS * (6 + 2 + 5 * C_) * 4
+        kern = {}
+        if fused:
+            kern["fused"] = k1_ms
+        else:
+            kern["K1"], kern["K3"] = k1_ms, k3_ms
+        kernels = {}
+        for name, ms in kern.items():
+            nbytes = per_field[name] * Fb + ill_b
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            kernels[name] = {"ms_per_launch": ms, "gbs": gbs, "frac": gbs / peak,
+                             "bytes_per_field": per_field[name], "illum_bytes_per_launch": ill_b,
+                             "survey_8d_gbs_illum_per_field": (per_field[name] + ill_b) * Fb / (ms * 1e-3) / 1e9}
+        dom = max(kern, key=kern.get)
+        names = {"K1": "preprocess_vec_kernel", "K3": "object_stats_scan_kernel (+init +compact)",
+                 "fused": "field_fused_kernel (+init +compact)"}
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 with open(tp) as f:
-                    traffic = json.load(f).get("K1" if k1_ms >= k3_ms else "K3")
+                    traffic = json.load(f).get(dom)
             except Exception:
                 traffic = None
         line = {
@@ -389,14 +418,15 @@ def gpu_arm(args):
             "config": {"workload": WORKLOAD, "fields_per_step": Fb, "bin": BIN, "n_cells": NCELLS,
                        "ring_fields": R, "l2": "inputs larger than L2: ring of %d distinct fields = %.1f GB" % (
                            R, R * (C_ * Z_ * H_ * W_ * 2 + H_ * W_ * 4) / 1e9),
+                       "mode": args.mode,
                        "sharding": "fields by well across ranks, no data-path collective"},
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ga, "peak": peak, "unit": "GB/s",
-                         "frac": ga / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": kb1 if k1_ms >= k3_ms else kb3},
-            "kernels": {"K1": {"ms_per_launch": k1_ms, "gbs": g1, "frac": g1 / peak, "bytes_per_field": kb1 // Fb},
-                        "K3": {"ms_per_launch": k3_ms, "gbs": g3, "frac": g3 / peak, "bytes_per_field": kb3 // Fb}},
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": kernels[dom]["gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": per_field[dom] * Fb + ill_b},
+            "kernels": kernels,
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "objects_last_field": int(n_obj_last[-1]),
@@ -413,6 +443,8 @@ def main():
     ap.add_argument("--steps", type=int, default=216)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fused", choices=["fused", "split"],
+                    help="fused: one K1+K3 pass per step (ips_field_fused); split: K1 then K3")
     ap.add_argument("--batch", type=int, default=16, help="fields per step")
     ap.add_argument("--ring", type=int, default=32, help="distinct device-resident fields")
     ap.add_argument("--e2e-batch", type=int, default=4)

@@ -44,9 +44,9 @@ PROTOTYPES = {
     "ips_field_fused": (i, [p, p, p, p, p, i, f, p, p, p, i, p, sz, i, i, i, i, i, p]),
     "ips_illum_accumulate": (i, [p, p, i, i, i, i, p]),
     "ips_illum_finalize_workspace_bytes": (sz, [i, i, i]),
-    "ips_illum_finalize": (i, [p, u64, f, f, p, p, sz, i, i, i, p]),
+    "ips_illum_finalize": (i, [p, u64, C.c_double, C.c_double, p, p, sz, i, i, i, p]),
     "ips_illum_median": (i, [p, p, i, i, i, i, p]),
-    "ips_illum_smooth_rescale": (i, [p, f, f, p, p, sz, i, i, i, p]),
+    "ips_illum_smooth_rescale": (i, [p, C.c_double, C.c_double, p, p, sz, i, i, i, p]),
     "ips_lanczos_workspace_bytes": (sz, [i, i, i, i, i]),
     "ips_lanczos_resize_u16": (i, [p, p, i, i, i, i, i, p, sz, p]),
     "ips_ring_sums": (i, [p, p, p, i, i, i, i, p]),

@@ -1,0 +1,138 @@
+// The one collective of the path: an all-gather of per-object feature rows for well-level
+// aggregation and normalisation (north_star; parity target Normalize_CP_ami.py:126,
+// Pycyto_pertime.py:69-72 -- the reference itself has no collective).
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2, which resolves to the copy PyTorch has
+// already loaded when the process uses torch.distributed) so that libips.so itself has no
+// link-time dependency on it.  The communicator is created from a unique id that the host
+// side broadcasts over its existing control plane (torch.distributed in this repository).
+#include <dlfcn.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "ips_common.cuh"
+
+namespace ips {
+
+// Minimal NCCL ABI (nccl.h: stable since 2.x)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt8 = 0, ncclInt64 = 4 };
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+static NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) return;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  });
+  return api;
+}
+
+struct Comm {
+  ncclComm_t nccl = nullptr;
+  int rank = 0, world = 1;
+  int64_t* d_counts = nullptr;   // [world] staging for the row-count exchange
+};
+
+#define IPS_NCCL_OK(expr)                                                                   \
+  do {                                                                                      \
+    ncclResult_t r__ = (expr);                                                              \
+    if (r__ != 0) IPS_FAIL(IPS_ERR_NCCL, "%s failed: %s", #expr, nccl().GetErrorString(r__)); \
+  } while (0)
+
+__global__ void set_count_kernel(int64_t* dst, int64_t v) { *dst = v; }
+
+}  // namespace ips
+
+using namespace ips;
+
+extern "C" int ips_comm_unique_id_bytes(void) { return (int)sizeof(ncclUniqueId); }
+
+extern "C" int ips_comm_unique_id(void* out, int bytes) {
+  if (out == nullptr || bytes < (int)sizeof(ncclUniqueId))
+    IPS_FAIL(IPS_ERR_BAD_ARG, "ips_comm_unique_id: need a %zu-byte buffer", sizeof(ncclUniqueId));
+  if (!nccl().ok) IPS_FAIL(IPS_ERR_NCCL, "ips_comm_unique_id: libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  IPS_NCCL_OK(nccl().GetUniqueId(&id));
+  memcpy(out, &id, sizeof(id));
+  return IPS_OK;
+}
+
+extern "C" int ips_comm_create(void** out, const void* unique_id, int bytes, int rank, int world) {
+  if (out == nullptr || unique_id == nullptr || bytes < (int)sizeof(ncclUniqueId))
+    IPS_FAIL(IPS_ERR_BAD_ARG, "ips_comm_create: bad arguments");
+  if (world < 1 || rank < 0 || rank >= world) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_comm_create: bad rank %d of %d", rank, world);
+  if (!nccl().ok) IPS_FAIL(IPS_ERR_NCCL, "ips_comm_create: libnccl.so.2 could not be loaded");
+  Comm* c = new Comm();
+  c->rank = rank;
+  c->world = world;
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  ncclResult_t r = nccl().CommInitRank(&c->nccl, world, id, rank);
+  if (r != 0) {
+    delete c;
+    IPS_FAIL(IPS_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r));
+  }
+  cudaError_t e = cudaMalloc(&c->d_counts, (size_t)world * sizeof(int64_t));
+  if (e != cudaSuccess) {
+    nccl().CommDestroy(c->nccl);
+    delete c;
+    IPS_FAIL(IPS_ERR_NOMEM, "ips_comm_create: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return IPS_OK;
+}
+
+extern "C" int ips_comm_destroy(void* comm) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  if (c == nullptr) return IPS_OK;
+  cudaFree(c->d_counts);
+  if (c->nccl) nccl().CommDestroy(c->nccl);
+  delete c;
+  return IPS_OK;
+}
+
+// all_rows [world][cap_per_rank][row_bytes]: rank r's rows land in block r (first counts[r]
+// rows valid).  counts_dev [world] int64 on the device receives every rank's row count.
+extern "C" int ips_allgather_rows(void* comm, const void* local_rows, int64_t n_local, int row_bytes,
+                                  void* all_rows, int64_t* counts_dev, int64_t cap_per_rank,
+                                  ips_stream_t stream) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  if (c == nullptr || all_rows == nullptr || counts_dev == nullptr)
+    IPS_FAIL(IPS_ERR_BAD_ARG, "ips_allgather_rows: NULL argument");
+  if (n_local < 0 || n_local > cap_per_rank || row_bytes <= 0)
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_allgather_rows: n_local=%lld cap=%lld row_bytes=%d", (long long)n_local,
+             (long long)cap_per_rank, row_bytes);
+  if (n_local > 0 && local_rows == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_allgather_rows: NULL rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t block = (size_t)cap_per_rank * row_bytes;
+  char* mine = reinterpret_cast<char*>(all_rows) + (size_t)c->rank * block;
+  // stage the local rows in their own block (in place all-gather), then one ncclAllGather
+  if (n_local > 0 && mine != local_rows)
+    IPS_CUDA_OK(cudaMemcpyAsync(mine, local_rows, (size_t)n_local * row_bytes, cudaMemcpyDeviceToDevice, st));
+  set_count_kernel<<<1, 1, 0, st>>>(c->d_counts + c->rank, n_local);
+  IPS_LAUNCH_OK("set_count_kernel");
+  IPS_NCCL_OK(nccl().AllGather(c->d_counts + c->rank, c->d_counts, sizeof(int64_t), ncclInt8, c->nccl, st));
+  IPS_CUDA_OK(cudaMemcpyAsync(counts_dev, c->d_counts, (size_t)c->world * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  IPS_NCCL_OK(nccl().AllGather(mine, all_rows, block, ncclInt8, c->nccl, st));
+  return IPS_OK;
+}

@@ -77,6 +77,14 @@ __device__ __forceinline__ void stg64_stream(void* ptr, uint2 v, uint64_t pol) {
                :: "l"(ptr), "r"(v.x), "r"(v.y), "l"(pol)
                : "memory");
 }
+// x / d as MUFU.RCP + FMUL (about 2 ulp).  __fdividef adds a range-scaling prologue of three
+// more instructions per quotient that the streaming kernels cannot afford; illumination
+// functions are O(1), far from the denormal / 2^126 ranges that prologue protects.
+__device__ __forceinline__ float fast_div(float x, float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return x * r;
+}
 // max of packed uint16 pairs
 __device__ __forceinline__ uint32_t vmax_u16x2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 __device__ __forceinline__ uint4 vmax_u16x8(uint4 a, uint4 b) {

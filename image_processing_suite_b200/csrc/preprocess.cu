@@ -158,7 +158,7 @@ preprocess_vec_kernel(const uint16_t* __restrict__ raw, const float* __restrict_
                             __uint_as_float(il[r][1].x), __uint_as_float(il[r][1].y),
                             __uint_as_float(il[r][1].z), __uint_as_float(il[r][1].w)};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = __fdividef(x[i], d[i]);
+        for (int i = 0; i < 8; ++i) q[i] = fast_div(x[i], d[i]);
         if (corrected != nullptr) {
           float* cp = corrected + fc * plane + (size_t)(y0 + r) * W + x0;
           stg128_stream(cp, make_uint4(__float_as_uint(q[0]), __float_as_uint(q[1]),
@@ -269,7 +269,7 @@ preprocess_scalar_kernel(const uint16_t* __restrict__ raw, const float* __restri
         if (maxproj != nullptr) maxproj[fc * plane + off] = (uint16_t)m;
         if (HAS_ILLUM) {
           const float d = illum[(size_t)c * plane + off];
-          const float q = __fdividef((float)m, d);
+          const float q = fast_div((float)m, d);
           if (corrected != nullptr) corrected[fc * plane + off] = q;
           fs += q;
           if (PCT) pct_merge(pmax, pcnt, (double)m / (double)d, 1ull);

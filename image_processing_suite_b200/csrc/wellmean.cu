@@ -1,0 +1,96 @@
+// Well-level aggregation of per-object rows: df.groupby("Metadata_Well").agg("mean")
+// (Normalize_CP_ami.py:126, Pycyto_pertime.py:69-72) -- the consumer of the all-gather.
+//
+// rows [N][D] float32 with a well id per row -> per-well float64 means.  Each block walks a
+// contiguous chunk of rows, thread d owns feature column d; consecutive rows of one well
+// (the common layout: rows arrive grouped by field, fields by well) are folded in a register
+// and flushed with one float64 atomic per (well, column) run.
+#include "ips_common.cuh"
+
+namespace ips {
+
+constexpr int WM_ROWS = 256;   // rows per block
+
+__global__ void well_zero_kernel(double* sums, int* counts, size_t n_sums, int n_wells) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_sums) sums[i] = 0.0;
+  if (i < (size_t)n_wells) counts[i] = 0;
+}
+
+__global__ void well_accumulate_kernel(const float* __restrict__ rows, const int32_t* __restrict__ well,
+                                       double* __restrict__ sums, int* __restrict__ counts,
+                                       int N, int D, int n_wells) {
+  const int r0 = blockIdx.x * WM_ROWS;
+  const int r1 = min(N, r0 + WM_ROWS);
+  for (int d = threadIdx.x; d < D + 1; d += blockDim.x) {   // column D = the row counter
+    int cur = -1;
+    double acc = 0.0;
+    int cnt = 0;
+    for (int r = r0; r < r1; ++r) {
+      const int w = well[r];
+      if (w < 0 || w >= n_wells) continue;   // rows without a well (id out of range) are dropped
+      if (w != cur) {
+        if (cur >= 0) {
+          if (d < D) atomicAdd(&sums[(size_t)cur * D + d], acc);
+          else atomicAdd(&counts[cur], cnt);
+        }
+        cur = w;
+        acc = 0.0;
+        cnt = 0;
+      }
+      if (d < D) acc += (double)rows[(size_t)r * D + d];
+      else ++cnt;
+    }
+    if (cur >= 0) {
+      if (d < D) atomicAdd(&sums[(size_t)cur * D + d], acc);
+      else atomicAdd(&counts[cur], cnt);
+    }
+  }
+}
+
+__global__ void well_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ counts,
+                                     double* __restrict__ mean_out, int32_t* __restrict__ count_out,
+                                     int n_wells, int D) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n_wells * D) return;
+  const int w = (int)(i / D);
+  const int c = counts[w];
+  mean_out[i] = c > 0 ? sums[i] / (double)c : __longlong_as_double(0x7ff8000000000000ll);
+  if (i % D == 0) count_out[w] = c;
+}
+
+static size_t wm_sums_bytes(int n_wells, int D) { return round_up((size_t)n_wells * D * sizeof(double), 256); }
+static size_t wm_counts_bytes(int n_wells) { return round_up((size_t)n_wells * sizeof(int), 256); }
+
+}  // namespace ips
+
+using namespace ips;
+
+extern "C" size_t ips_well_mean_workspace_bytes(int n_wells, int D) {
+  if (n_wells <= 0 || D <= 0) return 0;
+  return wm_sums_bytes(n_wells, D) + wm_counts_bytes(n_wells);
+}
+
+extern "C" int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
+                             int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream) {
+  if (!mean_out || !count_out || !ws) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_mean: NULL pointer argument");
+  if (N > 0 && (!rows || !well)) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_mean: NULL rows");
+  if (N < 0 || D <= 0 || n_wells <= 0) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_mean: bad shape N=%d D=%d n_wells=%d", N, D, n_wells);
+  const size_t need = ips_well_mean_workspace_bytes(n_wells, D);
+  if (ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "ips_well_mean: needs %zu workspace bytes (got %zu)", need, ws_bytes);
+  if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_well_mean: workspace not 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* sums = reinterpret_cast<double*>(ws);
+  int* counts = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + wm_sums_bytes(n_wells, D));
+  const size_t n_sums = (size_t)n_wells * D;
+  well_zero_kernel<<<(unsigned)((n_sums + 255) / 256), 256, 0, st>>>(sums, counts, n_sums, n_wells);
+  IPS_LAUNCH_OK("well_zero_kernel");
+  if (N > 0) {
+    const int threads = D + 1 <= 32 ? 32 : (D + 1 <= 64 ? 64 : (D + 1 <= 128 ? 128 : 256));
+    well_accumulate_kernel<<<(N + WM_ROWS - 1) / WM_ROWS, threads, 0, st>>>(rows, well, sums, counts, N, D, n_wells);
+    IPS_LAUNCH_OK("well_accumulate_kernel");
+  }
+  well_finalize_kernel<<<(unsigned)((n_sums + 255) / 256), 256, 0, st>>>(sums, counts, mean_out, count_out, n_wells, D);
+  IPS_LAUNCH_OK("well_finalize_kernel");
+  return IPS_OK;
+}

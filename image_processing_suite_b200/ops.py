@@ -153,3 +153,185 @@ def object_stats(labels, maxproj, illum=None, intensity_scale=1.0, n_max=None, o
                       _ptr(n_obj), _ptr(ints), _ptr(flts), n_max, _ptr(ws), ws.numel(), F, Cn, H, W,
                       _stream(dev))
     return {"n_objects": n_obj, "ints": ints, "flts": flts, "ws": ws}
+
+
+# ---- K2 ---------------------------------------------------------------------------------
+class IllumEstimator:
+    """Streaming per-plate illumination-function estimation (K2).
+
+    ``add(maxproj [F][C][H][W] uint16)`` folds a batch of max-projected fields into exact
+    uint32 per-pixel sums; ``finalize(sigma, robust_frac)`` returns the function
+    [C][H][W] float32 (mean -> edge-normalised Gaussian -> robust-minimum rescale, >= 1).
+    Produces what Illumination_QC_mult.py:186-193 loads as ``{ch}_illum.npy``.
+    """
+
+    MAX_FIELDS = 65537      # 65537 * 65535 < 2^32: the uint32 sums cannot overflow
+
+    def __init__(self, C_, H, W, device="cuda"):
+        self.dev = torch.device(device)
+        self.shape = (int(C_), int(H), int(W))
+        self.acc = torch.zeros(self.shape, dtype=torch.uint32, device=self.dev)
+        self.n = 0
+
+    def add(self, maxproj):
+        _check(maxproj, "maxproj", torch.uint16, 4, self.acc.device)
+        if tuple(maxproj.shape[1:]) != self.shape:
+            raise ValueError("maxproj shape %s does not match %s" % (tuple(maxproj.shape), self.shape))
+        F = maxproj.shape[0]
+        if self.n + F > self.MAX_FIELDS:
+            raise OverflowError("more than %d fields would overflow the uint32 sums" % self.MAX_FIELDS)
+        if F:
+            with torch.cuda.device(self.acc.device):
+                capi.call("ips_illum_accumulate", _ptr(maxproj), _ptr(self.acc), F, *self.shape,
+                          _stream(self.acc.device))
+        self.n += F
+        return self
+
+    def finalize(self, sigma, robust_frac=0.02):
+        if self.n == 0:
+            raise ValueError("no fields accumulated")
+        Cn, H, W = self.shape
+        dev = self.acc.device
+        with torch.cuda.device(dev):
+            out = torch.empty(self.shape, dtype=torch.float32, device=dev)
+            nbytes = capi.call("ips_illum_finalize_workspace_bytes", Cn, H, W)
+            ws = _workspace(nbytes, dev)
+            capi.call("ips_illum_finalize", _ptr(self.acc), self.n, float(sigma), float(robust_frac),
+                      _ptr(out), _ptr(ws), ws.numel(), Cn, H, W, _stream(dev))
+        return out
+
+
+def illum_median(stack):
+    """Per-pixel median over a device-resident stack [N][C][H][W] uint16 -> float32 [C][H][W]."""
+    _check(stack, "stack", torch.uint16, 4)
+    N, Cn, H, W = stack.shape
+    if N == 0:
+        raise ValueError("empty stack")
+    dev = stack.device
+    with torch.cuda.device(dev):
+        out = torch.empty((Cn, H, W), dtype=torch.float32, device=dev)
+        capi.call("ips_illum_median", _ptr(stack), _ptr(out), N, Cn, H, W, _stream(dev))
+    return out
+
+
+def illum_smooth_rescale(raw, sigma, robust_frac=0.02):
+    """Gaussian smoothing + robust-minimum rescale of a raw function [C][H][W] float32."""
+    _check(raw, "raw", torch.float32, 3)
+    Cn, H, W = raw.shape
+    dev = raw.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(raw)
+        ws = _workspace(capi.call("ips_illum_finalize_workspace_bytes", Cn, H, W), dev)
+        capi.call("ips_illum_smooth_rescale", _ptr(raw), float(sigma), float(robust_frac), _ptr(out),
+                  _ptr(ws), ws.numel(), Cn, H, W, _stream(dev))
+    return out
+
+
+# ---- K5 ---------------------------------------------------------------------------------
+def lanczos_resize_u16(planes, out_hw):
+    """Pillow-exact LANCZOS resize of uint16 planes [C][H][W] -> [C][outH][outW] (K5).
+    Replaces ``img.resize(target, resample=LANCZOS)`` of Image_re-binning.py:18."""
+    _check(planes, "planes", torch.uint16, 3)
+    Cn, H, W = planes.shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if oh <= 0 or ow <= 0:
+        raise ValueError("target size must be positive")
+    dev = planes.device
+    with torch.cuda.device(dev):
+        out = torch.empty((Cn, oh, ow), dtype=torch.uint16, device=dev)
+        if Cn:
+            ws = _workspace(capi.call("ips_lanczos_workspace_bytes", Cn, H, W, oh, ow), dev)
+            capi.call("ips_lanczos_resize_u16", _ptr(planes), _ptr(out), Cn, H, W, oh, ow, _ptr(ws),
+                      ws.numel(), _stream(dev))
+    return out
+
+
+# ---- K6 ---------------------------------------------------------------------------------
+def ring_sums(spec, n_rings):
+    """Ring sums of |z| and |z|^2 over the folded FFT radius (Illumination_QC_mult.py:61-68).
+    spec [F][H][W] complex128 -> (mag [F][n_rings], pow [F][n_rings]) float64."""
+    _check(spec, "spec", torch.complex128, 3)
+    F, H, W = spec.shape
+    dev = spec.device
+    with torch.cuda.device(dev):
+        mag = torch.empty((F, n_rings), dtype=torch.float64, device=dev)
+        pw = torch.empty((F, n_rings), dtype=torch.float64, device=dev)
+        if F and n_rings > 0:
+            capi.call("ips_ring_sums", _ptr(spec), _ptr(mag), _ptr(pw), int(n_rings), F, H, W, _stream(dev))
+    return mag, pw
+
+
+# ---- well aggregation -------------------------------------------------------------------
+def well_mean(rows, well, n_wells):
+    """Per-well mean of object rows [N][D] float32 with well ids [N] int32 in [0, n_wells).
+    Returns (mean [n_wells][D] float64, NaN for empty wells; count [n_wells] int32).
+    Replaces groupby('Metadata_Well').agg('mean') of Normalize_CP_ami.py:126."""
+    _check(rows, "rows", torch.float32, 2)
+    dev = rows.device
+    _check(well, "well", torch.int32, 1, dev)
+    N, D = rows.shape
+    if well.shape[0] != N:
+        raise ValueError("one well id per row expected")
+    with torch.cuda.device(dev):
+        mean = torch.empty((n_wells, D), dtype=torch.float64, device=dev)
+        count = torch.empty((n_wells,), dtype=torch.int32, device=dev)
+        ws = _workspace(capi.call("ips_well_mean_workspace_bytes", n_wells, D), dev)
+        capi.call("ips_well_mean", _ptr(rows), _ptr(well), _ptr(mean), _ptr(count), N, D, n_wells,
+                  _ptr(ws), ws.numel(), _stream(dev))
+    return mean, count
+
+
+# ---- K1 + K3 in one pass ------------------------------------------------------------------
+def field_fused(raw, illum, labels, bin=2, intensity_scale=1.0, n_max=None, want_maxproj=True,
+                want_binned=True, out=None):
+    """One pass over a batch of fields: max projection, b x b sum bin (of the corrected image
+    when illum is given) and per-object statistics over the label masks.
+
+    raw [F][C][Z][H][W] uint16, illum [C][H][W] float32 or None, labels [F][H][W] int32.
+    Returns dict with ``maxproj``, ``binned`` (as preprocess_fused) and ``n_objects``,
+    ``ints``, ``flts`` (as object_stats).  Same results as the two separate calls.
+    """
+    _check(raw, "raw", torch.uint16, 5)
+    dev = raw.device
+    F, Cn, Z, H, W = raw.shape
+    _check(labels, "labels", torch.int32, 3, dev)
+    if tuple(labels.shape) != (F, H, W):
+        raise ValueError("labels shape %s does not match raw %s" % (tuple(labels.shape), tuple(raw.shape)))
+    if illum is not None:
+        _check(illum, "illum", torch.float32, 3, dev)
+        if tuple(illum.shape) != (Cn, H, W):
+            raise ValueError("illum shape mismatch")
+    if bin not in (1, 2, 4):
+        raise ValueError("bin must be 1, 2 or 4")
+    if H % bin or W % bin:
+        raise ValueError("image size %dx%d is not divisible by bin %d" % (H, W, bin))
+    if n_max is None:
+        n_max = int(labels.max().item()) if labels.numel() else 0
+    n_max = max(int(n_max), 1)
+    out = dict(out or {})
+    with torch.cuda.device(dev):
+        mp = out.get("maxproj")
+        if mp is None and (want_maxproj or W % 8):
+            mp = torch.empty((F, Cn, H, W), dtype=torch.uint16, device=dev)
+        bn = out.get("binned")
+        if bn is None and want_binned:
+            bn = torch.empty((F, Cn, H // bin, W // bin),
+                             dtype=torch.float32 if illum is not None else torch.uint32, device=dev)
+        n_obj = out.get("n_objects")
+        if n_obj is None:
+            n_obj = torch.empty((F,), dtype=torch.int32, device=dev)
+        ints = out.get("ints")
+        if ints is None:
+            ints = torch.empty((F, n_max, 6), dtype=torch.int32, device=dev)
+        flts = out.get("flts")
+        if flts is None:
+            flts = torch.empty((F, n_max, 2 + 5 * Cn), dtype=torch.float32, device=dev)
+        ws_bytes = capi.call("ips_field_fused_workspace_bytes", F, Cn, H, W, bin, n_max)
+        ws = out.get("ws")
+        if ws is None or ws.numel() < ws_bytes:
+            ws = _workspace(ws_bytes, dev)
+        if F > 0:
+            capi.call("ips_field_fused", _ptr(raw), _ptr(illum), _ptr(labels), _ptr(mp), _ptr(bn), bin,
+                      float(intensity_scale), _ptr(n_obj), _ptr(ints), _ptr(flts), n_max, _ptr(ws),
+                      ws.numel(), F, Cn, Z, H, W, _stream(dev))
+    return {"maxproj": mp, "binned": bn, "n_objects": n_obj, "ints": ints, "flts": flts, "ws": ws}

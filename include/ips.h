@@ -98,6 +98,19 @@ int ips_object_stats(const int32_t* labels, const uint16_t* maxproj, const float
                      int Nmax, void* ws, size_t ws_bytes, int F, int C, int H, int W,
                      ips_stream_t stream);
 
+/* ---- K1 + K3 in one pass over the field -------------------------------------------------
+ * Same results as ips_preprocess_fused (maxproj, binned) followed by ips_object_stats on
+ * that max projection, without writing and re-reading it: the raw z-stack, the
+ * illumination function and the label mask are each read once.
+ * illum may be NULL (integer mode: uint32 bin sums, exact integer intensity sums).
+ * maxproj and binned may be NULL (outputs skipped).
+ */
+size_t ips_field_fused_workspace_bytes(int F, int C, int H, int W, int bin, int Nmax);
+int ips_field_fused(const uint16_t* raw, const float* illum, const int32_t* labels,
+                    uint16_t* maxproj, void* binned, int bin, float intensity_scale,
+                    int32_t* n_objects, int32_t* ints, float* flts, int Nmax, void* ws,
+                    size_t ws_bytes, int F, int C, int Z, int H, int W, ips_stream_t stream);
+
 /* ---- K2: per-plate illumination-function estimation ----------------------------------
  * Produces the {ch}_illum.npy functions that Illumination_QC_mult.py:186-193 and
  * Cellpose_GPU_s3fs.py:56 load (the reference computes them outside the repository).
@@ -109,7 +122,7 @@ int ips_object_stats(const int32_t* labels, const uint16_t* maxproj, const float
 int ips_illum_accumulate(const uint16_t* maxproj, uint32_t* acc, int F, int C, int H, int W,
                          ips_stream_t stream);
 size_t ips_illum_finalize_workspace_bytes(int C, int H, int W);
-int ips_illum_finalize(const uint32_t* acc, uint64_t n_fields, float sigma, float robust_frac,
+int ips_illum_finalize(const uint32_t* acc, uint64_t n_fields, double sigma, double robust_frac,
                        float* illum_out, void* ws, size_t ws_bytes, int C, int H, int W,
                        ips_stream_t stream);
 /* Per-pixel median over a device-resident stack (median mode): stack [N][C][H][W] uint16
@@ -117,7 +130,8 @@ int ips_illum_finalize(const uint32_t* acc, uint64_t n_fields, float sigma, floa
 int ips_illum_median(const uint16_t* stack, float* raw_out, int N, int C, int H, int W,
                      ips_stream_t stream);
 /* Gaussian + robust rescale on a float32 raw function (shared by mean and median mode). */
-int ips_illum_smooth_rescale(const float* raw, float sigma, float robust_frac, float* illum_out,
+/* (ws of ips_illum_finalize_workspace_bytes is large enough for this call too.) */
+int ips_illum_smooth_rescale(const float* raw, double sigma, double robust_frac, float* illum_out,
                              void* ws, size_t ws_bytes, int C, int H, int W, ips_stream_t stream);
 
 /* ---- K5: Pillow-exact LANCZOS resize of 16-bit planes -------------------------------
@@ -159,6 +173,22 @@ int ips_cosine_triu(const float* X, const int32_t* group, int n_groups, double* 
 size_t ips_well_mean_workspace_bytes(int n_wells, int D);
 int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
                   int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream);
+
+/* ---- the one collective: all-gather of per-object rows ----------------------------------
+ * north_star's "one NCCL all-gather of per-object feature rows for well-level aggregation
+ * and normalisation" (the reference has no collective; parity target is the pandas groupby
+ * of Normalize_CP_ami.py:126 over all rows).  NCCL is bound at run time (libnccl.so.2).
+ * The unique id is created on one rank and distributed by the caller's control plane.
+ * all_rows [world][cap_per_rank][row_bytes]: rank r's rows land in block r, the first
+ * counts_dev[r] of them valid; counts_dev [world] int64 (device).
+ */
+int ips_comm_unique_id_bytes(void);
+int ips_comm_unique_id(void* out, int bytes);
+int ips_comm_create(void** comm_out, const void* unique_id, int bytes, int rank, int world);
+int ips_comm_destroy(void* comm);
+int ips_allgather_rows(void* comm, const void* local_rows, int64_t n_local, int row_bytes,
+                       void* all_rows, int64_t* counts_dev, int64_t cap_per_rank,
+                       ips_stream_t stream);
 
 /* ---- host-buffer pipeline (the end-to-end call a script makes) -------------------------
  * One call = H2D of a batch of raw fields + label masks, K1, K3, D2H of max projections,

@@ -1,0 +1,121 @@
+"""Fused K1+K3 pass (ips_field_fused) vs the oracle and vs the two separate kernels.
+
+Bit-exact: max projection, integer bin sums, object count / label / area / bbox.
+RTOL = 1e-5: float bin sums, centroid, intensity moments.
+"""
+import numpy as np
+import pytest
+
+from image_processing_suite_b200 import synth
+from oracle import object_stats as o_obj
+from oracle import preprocess as o_pre
+from tests.gpu_util import dev, host, require_gpu
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _check_rows(res, f, lab, mp, ill, scale, C):
+    n = int(host(res["n_objects"])[f])
+    e_i, e_f = o_obj.object_stats(lab, mp, ill, scale)
+    assert n == e_i.shape[0]
+    np.testing.assert_array_equal(host(res["ints"])[f, :n], e_i)
+    got = host(res["flts"])[f, :n].astype(np.float64)
+    np.testing.assert_allclose(got[:, :2], e_f[:, :2], rtol=RTOL, atol=1e-6)
+    for c in range(C):
+        o = 2 + 5 * c
+        for k in (0, 1, 3, 4):
+            np.testing.assert_allclose(got[:, o + k], e_f[:, o + k], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(got[:, o + 2], e_f[:, o + 2], rtol=RTOL, atol=RTOL * np.abs(e_f[:, o + 1]).max())
+
+
+@pytest.mark.parametrize("shape,cells", [((2, 3, 3, 128, 160), 30), ((1, 5, 5, 96, 512), 40),
+                                         ((2, 2, 2, 64, 72), 8), ((1, 1, 4, 40, 264), 10)])
+@pytest.mark.parametrize("bin", [1, 2, 4])
+@pytest.mark.parametrize("with_illum", [True, False])
+def test_field_fused_matches_oracle(shape, cells, bin, with_illum):
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    F, C, Z, H, W = shape
+    labs = np.stack([synth.make_labels(H, W, cells, seed=70 + f, amin=5, amax=12) for f in range(F)])
+    raw = np.stack([synth.field_numpy(labs[f], c=C, z=Z, seed=f, saturate_frac=1e-3) for f in range(F)])
+    ill = synth.make_illum(C, H, W, seed=3) if with_illum else None
+    scale = 1.0 / 65535.0 if with_illum else 1.0
+    res = ops.field_fused(dev(raw), dev(ill) if with_illum else None, dev(labs), bin=bin,
+                          intensity_scale=scale, n_max=cells)
+    for f in range(F):
+        mp, _, binned = o_pre.preprocess_field(raw[f], ill, bin)
+        np.testing.assert_array_equal(host(res["maxproj"])[f], mp)
+        if with_illum:
+            np.testing.assert_allclose(host(res["binned"])[f], binned, rtol=RTOL)
+        else:
+            np.testing.assert_array_equal(host(res["binned"])[f], binned)
+        _check_rows(res, f, labs[f], mp, ill, scale, C)
+
+
+def test_field_fused_touching_objects_and_junctions():
+    """Confluent mask: every window on a boundary holds 2 labels, junction windows 3-4."""
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    H, W = 96, 256
+    yy, xx = np.mgrid[0:H, 0:W]
+    lab = (1 + (yy // 7) * 40 + (xx // 5)).astype(np.int32)      # 7 x 5 px tiles, all touching
+    lab[(yy + xx) % 11 == 0] = 0
+    rng = np.random.default_rng(4)
+    raw = rng.integers(0, 65536, (1, 2, 2, H, W), dtype=np.uint16)
+    ill = (1.0 + rng.random((2, H, W))).astype(np.float32)
+    n_max = int(lab.max())
+    res = ops.field_fused(dev(raw), dev(ill), dev(lab[None]), bin=2, n_max=n_max)
+    mp = raw[0].max(axis=1)
+    _check_rows(res, 0, lab, mp, ill, 1.0, 2)
+    sep = ops.object_stats(dev(lab[None]), dev(mp[None]), dev(ill), 1.0, n_max=n_max)
+    _check_rows(sep, 0, lab, mp, ill, 1.0, 2)
+
+
+def test_field_fused_one_huge_object_and_overflow():
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    H, W = 64, 512
+    lab = np.ones((1, H, W), np.int32)                       # runs longer than a tree segment
+    lab[0, :, 300:] = 2
+    rng = np.random.default_rng(5)
+    raw = rng.integers(0, 65536, (1, 1, 3, H, W), dtype=np.uint16)
+    res = ops.field_fused(dev(raw), None, dev(lab), bin=2, n_max=2)
+    _check_rows(res, 0, lab[0], raw[0].max(axis=1), None, 1.0, 1)
+    res2 = ops.field_fused(dev(raw), None, dev(lab), bin=2, n_max=1)
+    assert int(host(res2["n_objects"])[0]) == -1
+
+
+def test_field_fused_ragged_width_falls_back_to_general_kernels():
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    H, W = 36, 52
+    lab = synth.make_labels(H, W, 5, seed=2, amin=4, amax=7)[None]
+    rng = np.random.default_rng(6)
+    raw = rng.integers(0, 65536, (1, 2, 2, H, W), dtype=np.uint16)
+    ill = (1.0 + rng.random((2, H, W))).astype(np.float32)
+    res = ops.field_fused(dev(raw), dev(ill), dev(lab), bin=2, n_max=5)
+    mp, _, binned = o_pre.preprocess_field(raw[0], ill, 2)
+    np.testing.assert_array_equal(host(res["maxproj"])[0], mp)
+    np.testing.assert_allclose(host(res["binned"])[0], binned, rtol=RTOL)
+    _check_rows(res, 0, lab[0], mp, ill, 1.0, 2)
+
+
+def test_field_fused_equals_split_kernels_at_full_size():
+    """Config-2 size: the fused pass and K1 -> K3 must agree (integers exactly)."""
+    torch = require_gpu()
+    from image_processing_suite_b200 import ops
+    H = W = 2160
+    lab = dev(synth.make_labels(H, W, 2000, seed=321)[None])
+    g = torch.Generator(device="cuda").manual_seed(9)
+    raw = torch.randint(0, 65536, (1, 5, 3, H, W), device="cuda", generator=g, dtype=torch.int32).to(torch.uint16)
+    ill = dev(synth.make_illum(5, H, W, seed=1))
+    fz = ops.field_fused(raw, ill, lab, bin=2, intensity_scale=1 / 65535.0, n_max=2000)
+    k1 = ops.preprocess_fused(raw, ill, bin=2)
+    k3 = ops.object_stats(lab, k1["maxproj"], ill, 1 / 65535.0, n_max=2000)
+    assert bool((fz["maxproj"].view(torch.int16) == k1["maxproj"].view(torch.int16)).all())
+    assert bool(torch.allclose(fz["binned"], k1["binned"], rtol=1e-6))
+    n = int(fz["n_objects"][0])
+    assert n == int(k3["n_objects"][0]) == 2000
+    assert bool((fz["ints"][0, :n] == k3["ints"][0, :n]).all())
+    assert bool(torch.allclose(fz["flts"][0, :n], k3["flts"][0, :n], rtol=1e-5, atol=1e-7))
