@@ -17,8 +17,8 @@
 
 namespace ips {
 
-template <int BIN, int ZT, bool HAS_ILLUM>
-__global__ void __launch_bounds__(OA_THREADS, 2)
+template <int BIN, int ZT, bool HAS_ILLUM, int MINB>
+__global__ void __launch_bounds__(OA_THREADS, MINB)
 field_fused_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ illum,
                    const int32_t* __restrict__ labels, uint16_t* __restrict__ maxproj,
                    void* __restrict__ binned, unsigned long long* __restrict__ rec, int* __restrict__ flags,
@@ -185,8 +185,12 @@ template <int BIN, bool HAS_ILLUM>
 static void launch_fused(int Z, int grid, cudaStream_t st, const uint16_t* raw, const float* illum,
                          const int32_t* labels, uint16_t* maxproj, void* binned, unsigned long long* rec,
                          int* flags, int Nmax, int F, int C, int H, int W, int tiles_x) {
+  // Occupancy is what hides the latency here (measured on B200, profiles/README.md): 4 CTAs
+  // per SM (64 registers, no spills) beats 2 and 3 CTAs and a software-pipelined 1-CTA variant.
+  // BIN = 4 holds a 4 x 8 window per lane and needs the larger register budget.
+  constexpr int MINB = BIN == 4 ? 2 : 4;
 #define IPS_FF_CASE(ZT)                                                           \
-  field_fused_kernel<BIN, ZT, HAS_ILLUM><<<grid, OA_THREADS, 0, st>>>(            \
+  field_fused_kernel<BIN, ZT, HAS_ILLUM, MINB><<<grid, OA_THREADS, 0, st>>>(      \
       raw, illum, labels, maxproj, binned, rec, flags, Nmax, F, C, Z, H, W, tiles_x)
   switch (Z) {
     case 3: IPS_FF_CASE(3); break;

@@ -78,7 +78,7 @@ __device__ __forceinline__ void k3_load_chan(K3ChanRegs& R, const uint16_t* __re
 }
 
 template <bool HAS_ILLUM, bool VEC>
-__global__ void __launch_bounds__(OA_THREADS, 2)
+__global__ void __launch_bounds__(OA_THREADS, 4)
 object_stats_scan_kernel(const int32_t* __restrict__ labels, const uint16_t* __restrict__ maxproj,
                          const float* __restrict__ illum, unsigned long long* __restrict__ rec,
                          int* __restrict__ flags, int Nmax, int F, int C, int H, int W, int tiles_x) {
@@ -119,10 +119,7 @@ object_stats_scan_kernel(const int32_t* __restrict__ labels, const uint16_t* __r
       for (int i = 0; i < OA_PX; ++i) lab[r][i] = 0;
     }
   }
-  // channel 0 is requested together with the labels (it cannot wait for the label analysis
-  // without serialising two memory round trips); later channels skip all-background rows
-  K3ChanRegs cur, nxt;
-  k3_load_chan<HAS_ILLUM, VEC>(cur, mp, illum, 0, y0, x0, H, W, col_ok ? (1u << K3_ROWS) - 1u : 0u, pol_stream, pol_keep);
+  K3ChanRegs cur;
 
   bool overflow = false;
   OaLane<K3_ROWS> L;
@@ -152,17 +149,12 @@ object_stats_scan_kernel(const int32_t* __restrict__ labels, const uint16_t* __r
     }
     oa_channel<K3_ROWS, HAS_ILLUM>(L, c, fv, iv, sh, rec_f, C);
   };
+  // Occupancy (4 CTAs per SM at 64 registers) hides the load latency better than a second
+  // register set would (measured, profiles/README.md).  All-background rows are not loaded.
   if (__any_sync(OA_FULL, fg != 0u)) {
-    // two register sets in ping-pong: channel c + 1 is in flight while channel c is folded
-    for (int c = 0; c < C; c += 2) {
-      if (c + 1 < C)
-        k3_load_chan<HAS_ILLUM, VEC>(nxt, mp, illum, (size_t)(c + 1) * plane, y0, x0, H, W, row_need, pol_stream, pol_keep);
+    for (int c = 0; c < C; ++c) {
+      k3_load_chan<HAS_ILLUM, VEC>(cur, mp, illum, (size_t)c * plane, y0, x0, H, W, row_need, pol_stream, pol_keep);
       consume(cur, c);
-      if (c + 1 < C) {
-        if (c + 2 < C)
-          k3_load_chan<HAS_ILLUM, VEC>(cur, mp, illum, (size_t)(c + 2) * plane, y0, x0, H, W, row_need, pol_stream, pol_keep);
-        consume(nxt, c + 1);
-      }
     }
   }
   if (overflow) atomicOr(flags + f, 1);

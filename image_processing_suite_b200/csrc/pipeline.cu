@@ -1,7 +1,7 @@
 // Host-buffer pipeline: the end-to-end call a drop-in script makes for a batch of fields.
 //
-// One submit = H2D of the batch's raw z-stacks and label masks, K1 (fused preprocess),
-// K3 (per-object statistics), D2H of max projections, binned planes and object rows.
+// One submit = H2D of the batch's raw z-stacks and label masks, the fused field pass
+// (ips_field_fused: K1 + K3), D2H of max projections, binned planes and object rows.
 // Three streams (copy-in, compute, copy-out) and `depth` device slots chained by events,
 // so the copy-in of batch i+1 and the copy-out of batch i-1 overlap the kernels of batch
 // i (PCIe is full duplex).  The illumination function is uploaded once at creation: it is
@@ -92,7 +92,7 @@ extern "C" int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, i
     PIPE_CUDA_OK(cudaMalloc(&p->illum, (size_t)C * plane * sizeof(float)));
     PIPE_CUDA_OK(cudaMemcpy(p->illum, illum_host, (size_t)C * plane * sizeof(float), cudaMemcpyHostToDevice));
   }
-  p->ws_bytes = ips_object_stats_workspace_bytes(fields_per_batch, C, Nmax);
+  p->ws_bytes = ips_field_fused_workspace_bytes(fields_per_batch, C, H, W, bin, Nmax);
   p->slots.resize(depth);
   for (Slot& s : p->slots) {
     PIPE_CUDA_OK(cudaMalloc(&s.raw, Fb * C * Z * plane * sizeof(uint16_t)));
@@ -129,11 +129,9 @@ extern "C" int64_t ips_pipeline_submit(ips_pipeline_t* p, const uint16_t* raw_ho
                               cudaMemcpyHostToDevice, p->s_in));
   IPS_CUDA_OK(cudaEventRecord(s.h2d_done, p->s_in));
   IPS_CUDA_OK(cudaStreamWaitEvent(p->s_compute, s.h2d_done, 0));
-  int rc = ips_preprocess_fused(s.raw, p->illum, s.maxproj, nullptr, s.binned, p->bin, nullptr, nullptr,
-                                0, p->Fb, p->C, p->Z, p->H, p->W, p->s_compute);
-  if (rc != IPS_OK) return rc;
-  rc = ips_object_stats(s.labels, s.maxproj, p->illum, p->scale, s.n_objects, s.ints, s.flts, p->Nmax,
-                        s.ws, p->ws_bytes, p->Fb, p->C, p->H, p->W, p->s_compute);
+  const int rc = ips_field_fused(s.raw, p->illum, s.labels, s.maxproj, s.binned, p->bin, p->scale,
+                                 s.n_objects, s.ints, s.flts, p->Nmax, s.ws, p->ws_bytes, p->Fb, p->C,
+                                 p->Z, p->H, p->W, p->s_compute);
   if (rc != IPS_OK) return rc;
   IPS_CUDA_OK(cudaEventRecord(s.compute_done, p->s_compute));
   IPS_CUDA_OK(cudaStreamWaitEvent(p->s_out, s.compute_done, 0));

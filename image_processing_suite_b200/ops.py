@@ -335,3 +335,32 @@ def field_fused(raw, illum, labels, bin=2, intensity_scale=1.0, n_max=None, want
                       float(intensity_scale), _ptr(n_obj), _ptr(ints), _ptr(flts), n_max, _ptr(ws),
                       ws.numel(), F, Cn, Z, H, W, _stream(dev))
     return {"maxproj": mp, "binned": bn, "n_objects": n_obj, "ints": ints, "flts": flts, "ws": ws}
+
+
+# ---- K4 ---------------------------------------------------------------------------------
+def cosine_triu(X, group=None, n_groups=None):
+    """Per-group sum of strict-upper-triangle cosine similarities (K4).
+
+    X [N][D] float32 (NaN already replaced by 0); group [N] int32 with ascending ids
+    0..n_groups-1 (rows of a group contiguous) or None for a single group.
+    Returns (sum [n_groups] float64, npairs [n_groups] int64); mean = sum / npairs.
+    Replaces cosine_similarity -> triu(k=1) of Feature_select_cosine_ami.py:145-149.
+    """
+    _check(X, "X", torch.float32, 2)
+    dev = X.device
+    N, D = X.shape
+    if group is not None:
+        _check(group, "group", torch.int32, 1, dev)
+        if group.shape[0] != N:
+            raise ValueError("one group id per row expected")
+        if n_groups is None:
+            n_groups = int(group.max().item()) + 1 if N else 1
+    else:
+        n_groups = 1
+    with torch.cuda.device(dev):
+        s = torch.empty((n_groups,), dtype=torch.float64, device=dev)
+        npairs = torch.empty((n_groups,), dtype=torch.int64, device=dev)
+        ws = _workspace(capi.call("ips_cosine_workspace_bytes", max(N, 1), D), dev)
+        capi.call("ips_cosine_triu", _ptr(X), _ptr(group), int(n_groups), _ptr(s), _ptr(npairs), N, D,
+                  _ptr(ws), ws.numel(), _stream(dev))
+    return s, npairs

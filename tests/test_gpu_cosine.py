@@ -1,0 +1,58 @@
+"""K4 parity: replicate-group cosine similarity (CUDA) vs scikit-learn-pinned oracle.
+
+cos values live in [-1, 1]: ATOL = 1e-5 on the mean similarity of a group (north_star's
+1e-5 against the reference's float64), pair counts exact."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cosine as o_cos
+from tests.gpu_util import dev, host, require_gpu
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-5
+
+
+@pytest.mark.parametrize("case", ["g4", "g7", "g2", "g1"])
+def test_cosine_golden(golden_dir, case):
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    g = np.load(os.path.join(golden_dir, "cosine.npz"))
+    x = g[f"{case}_x"]
+    s, n = ops.cosine_triu(dev(x.astype(np.float32)))
+    ref = g[f"{case}_triu"]
+    assert int(host(n)[0]) == ref.size
+    if ref.size:
+        assert abs(float(host(s)[0]) / ref.size - float(g[f"{case}_mean"])) < ATOL
+    else:
+        assert float(host(s)[0]) == 0.0
+
+
+def test_cosine_grouped_matches_oracle():
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(11)
+    sizes = [3, 1, 7, 4, 2, 130, 5, 64, 65]
+    group = np.repeat(np.arange(len(sizes)), sizes).astype(np.int32)
+    x = rng.normal(size=(group.size, 300)).astype(np.float32)
+    x[4] = 0.0                                               # a zero row stays zero
+    x[10:14] += 5.0                                          # a tight group
+    s, n = ops.cosine_triu(dev(x), dev(group))
+    ref = o_cos.grouped_triu(x.astype(np.float64), group)
+    for gid, (rs, rn) in ref.items():
+        assert int(host(n)[gid]) == rn
+        if rn:
+            assert abs(float(host(s)[gid]) / rn - rs / rn) < ATOL
+
+
+def test_cosine_single_group_closed_form_large():
+    """Size-independent property: sum_{i<j} cos = (|sum x^|^2 - sum |x^|^2) / 2."""
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(12)
+    x = rng.normal(size=(3000, 700)).astype(np.float32) + 0.3
+    s, n = ops.cosine_triu(dev(x))
+    assert int(host(n)[0]) == 3000 * 2999 // 2
+    ref = o_cos.triu_sum_closed_form(x.astype(np.float64))
+    assert abs(float(host(s)[0]) - ref) / int(host(n)[0]) < ATOL
