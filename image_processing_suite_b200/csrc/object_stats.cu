@@ -12,8 +12,8 @@
 //                   reduction runs lane -> warp (segmented shuffle tree) -> CTA (record list
 //                   in shared memory) -> global accumulators (atomics, once per object and
 //                   256 x 16 tile); see object_accum.cuh.
-//   3. compact   -- one block per field: prefix-sum over "area > 0" and emit dense rows in
-//                   ascending label order, converting sums to mean / std / centroid.
+//   3. compact   -- prefix-sum over "area > 0" and emit dense rows in ascending label order,
+//                   converting sums to mean / std / centroid (256 labels per block).
 // Blocks are numbered field-fastest so that the blocks reading the same piece of the
 // plate-constant illumination function run together and share it through L2.
 #include "object_accum.cuh"
@@ -161,94 +161,101 @@ object_stats_scan_kernel(const int32_t* __restrict__ labels, const uint16_t* __r
   oa_finish<HAS_ILLUM>(sh, rec_f, C);
 }
 
-// One block per field: dense rows in ascending label order.
+// Dense rows in ascending label order.  Block (chunk, field) owns K3_CHUNK consecutive labels:
+// it counts the present labels before its chunk (that is its first row), ranks its own present
+// labels with a ballot prefix and converts sums to mean / std / centroid.  The last chunk
+// writes the field's object count.
+constexpr int K3_CHUNK = 256;
+
 template <bool HAS_ILLUM>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(K3_CHUNK)
 object_stats_compact_kernel(const unsigned long long* __restrict__ rec, const int* __restrict__ flags,
                             int32_t* __restrict__ n_objects, int32_t* __restrict__ ints,
                             float* __restrict__ flts, int Nmax, int C, float intensity_scale) {
-  const int f = blockIdx.x;
+  const int f = blockIdx.y;
+  const int chunk = blockIdx.x;
   const int words = k3_record_words(C);
   const int nf = 2 + 5 * C;
   const unsigned long long* rec_f = rec + (size_t)f * Nmax * words;
   int32_t* ints_f = ints + (size_t)f * Nmax * 6;
   float* flts_f = flts + (size_t)f * Nmax * nf;
-  __shared__ int warp_tot[32];
-  __shared__ int base_s;
-  if (threadIdx.x == 0) base_s = 0;
-  __syncthreads();
+  __shared__ int warp_cnt[K3_CHUNK / 32];
+  __shared__ int warp_tot[K3_CHUNK / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double sc = (double)intensity_scale;
-  for (int start = 0; start < Nmax; start += blockDim.x) {
-    const int li = start + threadIdx.x;  // label - 1
-    const unsigned* r32 = nullptr;
-    unsigned area = 0;
-    if (li < Nmax) {
-      r32 = reinterpret_cast<const unsigned*>(rec_f + (size_t)li * words);
-      area = r32[4];
-    }
-    const bool present = area > 0u;
-    const unsigned bal = __ballot_sync(0xffffffffu, present);
-    const int wpre = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    int wbase = 0, total = 0;
-    const int nw = blockDim.x >> 5;
-    for (int w = 0; w < nw; ++w) {
-      const int tcount = warp_tot[w];
-      if (w < warp) wbase += tcount;
-      total += tcount;
-    }
-    const int base = base_s;
-    if (present) {
-      const int row = base + wbase + wpre;
-      const unsigned long long* r = rec_f + (size_t)li * words;
-      int32_t* o = ints_f + (size_t)row * 6;
-      o[0] = li + 1;
-      o[1] = (int)area;
-      o[2] = (int)r32[5];
-      o[3] = (int)r32[6];
-      o[4] = (int)r32[7];
-      o[5] = (int)r32[8];
-      float* q = flts_f + (size_t)row * nf;
-      const double n = (double)area;
-      q[0] = (float)((double)r[0] / n);
-      q[1] = (float)((double)r[1] / n);
-      for (int c = 0; c < C; ++c) {
-        double s, mean, var;
-        float mn, mx;
-        if (HAS_ILLUM) {
-          s = __longlong_as_double((long long)r[5 + 3 * c]);
-          const double sq = __longlong_as_double((long long)r[6 + 3 * c]);
-          mean = s / n;
-          var = sq / n - mean * mean;
-          mn = __uint_as_float(r32[2 * (7 + 3 * c)]);
-          mx = __uint_as_float(r32[2 * (7 + 3 * c) + 1]);
-        } else {
-          const unsigned long long is = r[5 + 3 * c], isq = r[6 + 3 * c];
-          s = (double)is;
-          mean = s / n;
-          // exact integer numerator n*sum(x^2) - (sum x)^2, so constant objects give 0
-          const unsigned __int128 num = (unsigned __int128)isq * area - (unsigned __int128)is * is;
-          var = (double)(unsigned long long)(num >> 32) * 4294967296.0 + (double)(unsigned)(num & 0xffffffffu);
-          var = var / (n * n);
-          mn = (float)r32[2 * (7 + 3 * c)];
-          mx = (float)r32[2 * (7 + 3 * c) + 1];
-        }
-        if (!(var > 0.0)) var = 0.0;
-        float* qc = q + 2 + 5 * c;
-        qc[0] = (float)(s * sc);
-        qc[1] = (float)(mean * sc);
-        qc[2] = (float)(sqrt(var) * sc);
-        qc[3] = (float)((double)mn * sc);
-        qc[4] = (float)((double)mx * sc);
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) base_s = base + total;
-    __syncthreads();
+
+  // rows taken by the labels of earlier chunks
+  int before = 0;
+  for (int li = threadIdx.x; li < chunk * K3_CHUNK; li += K3_CHUNK)
+    before += reinterpret_cast<const unsigned*>(rec_f + (size_t)li * words)[4] > 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 0) warp_cnt[warp] = before;
+
+  const int li = chunk * K3_CHUNK + threadIdx.x;  // label - 1
+  const unsigned* r32 = nullptr;
+  unsigned area = 0;
+  if (li < Nmax) {
+    r32 = reinterpret_cast<const unsigned*>(rec_f + (size_t)li * words);
+    area = r32[4];
   }
-  if (threadIdx.x == 0) n_objects[f] = flags[f] ? -1 : base_s;
+  const bool present = area > 0u;
+  const unsigned bal = __ballot_sync(0xffffffffu, present);
+  const int wpre = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < K3_CHUNK / 32; ++w) {
+    base += warp_cnt[w];
+    if (w < warp) wbase += warp_tot[w];
+    total += warp_tot[w];
+  }
+  const double sc = (double)intensity_scale;
+  if (present) {
+    const int row = base + wbase + wpre;
+    const unsigned long long* r = rec_f + (size_t)li * words;
+    int32_t* o = ints_f + (size_t)row * 6;
+    o[0] = li + 1;
+    o[1] = (int)area;
+    o[2] = (int)r32[5];
+    o[3] = (int)r32[6];
+    o[4] = (int)r32[7];
+    o[5] = (int)r32[8];
+    float* q = flts_f + (size_t)row * nf;
+    const double n = (double)area;
+    q[0] = (float)((double)r[0] / n);
+    q[1] = (float)((double)r[1] / n);
+    for (int c = 0; c < C; ++c) {
+      double s, mean, var;
+      float mn, mx;
+      if (HAS_ILLUM) {
+        s = __longlong_as_double((long long)r[5 + 3 * c]);
+        const double sq = __longlong_as_double((long long)r[6 + 3 * c]);
+        mean = s / n;
+        var = sq / n - mean * mean;
+        mn = __uint_as_float(r32[2 * (7 + 3 * c)]);
+        mx = __uint_as_float(r32[2 * (7 + 3 * c) + 1]);
+      } else {
+        const unsigned long long is = r[5 + 3 * c], isq = r[6 + 3 * c];
+        s = (double)is;
+        mean = s / n;
+        // exact integer numerator n*sum(x^2) - (sum x)^2, so constant objects give 0
+        const unsigned __int128 num = (unsigned __int128)isq * area - (unsigned __int128)is * is;
+        var = (double)(unsigned long long)(num >> 32) * 4294967296.0 + (double)(unsigned)(num & 0xffffffffu);
+        var = var / (n * n);
+        mn = (float)r32[2 * (7 + 3 * c)];
+        mx = (float)r32[2 * (7 + 3 * c) + 1];
+      }
+      if (!(var > 0.0)) var = 0.0;
+      float* qc = q + 2 + 5 * c;
+      qc[0] = (float)(s * sc);
+      qc[1] = (float)(mean * sc);
+      qc[2] = (float)(sqrt(var) * sc);
+      qc[3] = (float)((double)mn * sc);
+      qc[4] = (float)((double)mx * sc);
+    }
+  }
+  if (chunk == (int)gridDim.x - 1 && threadIdx.x == 0) n_objects[f] = flags[f] ? -1 : base + total;
 }
 
 static size_t k3_records_bytes(int F, int C, int Nmax) {
@@ -269,10 +276,11 @@ int k3_launch_init(unsigned long long* rec, int* flags, int F, int C, int Nmax, 
 
 int k3_launch_compact(const unsigned long long* rec, const int* flags, int32_t* n_objects, int32_t* ints,
                       float* flts, int Nmax, int F, int C, float intensity_scale, bool has_illum, cudaStream_t st) {
+  if (F > 65535) IPS_FAIL(IPS_ERR_BAD_SHAPE, "object statistics: at most 65535 fields per call (got %d)", F);
   if (has_illum)
-    object_stats_compact_kernel<true><<<F, 1024, 0, st>>>(rec, flags, n_objects, ints, flts, Nmax, C, intensity_scale);
+    object_stats_compact_kernel<true><<<dim3((Nmax + K3_CHUNK - 1) / K3_CHUNK, F), K3_CHUNK, 0, st>>>(rec, flags, n_objects, ints, flts, Nmax, C, intensity_scale);
   else
-    object_stats_compact_kernel<false><<<F, 1024, 0, st>>>(rec, flags, n_objects, ints, flts, Nmax, C, intensity_scale);
+    object_stats_compact_kernel<false><<<dim3((Nmax + K3_CHUNK - 1) / K3_CHUNK, F), K3_CHUNK, 0, st>>>(rec, flags, n_objects, ints, flts, Nmax, C, intensity_scale);
   IPS_LAUNCH_OK("object_stats_compact_kernel");
   return IPS_OK;
 }

@@ -1,0 +1,210 @@
+"""Drop-in for Illumination_QC_mult.py: same flags, same functions, same output columns.
+
+Per site x channel: read the TIFF, divide by the pre-loaded illumination function
+(Illumination_QC_mult.py:145-150), ImageQuality_PowerLogLogSlope (rps, :31-70, :104-116) and
+ImageQuality_PercentMaximal (:73-95).  On the device: the divide and the spectrum are float64
+(torch.fft is the FFT library, as scipy.fftpack is in the reference), the ring-keyed sums are
+ips_ring_sums, PercentMaximal is the float64 side reduction of ips_preprocess_fused.
+Error convention unchanged: process_site never raises; failures become QC_Error_{ch} strings.
+"""
+import argparse
+import concurrent.futures
+import logging
+import os
+import threading
+
+import numpy as np
+import pandas as pd
+
+from . import tiffio
+
+
+def parse_args(argv=None):
+    parser = argparse.ArgumentParser(description="CellProfiler-Matched Image QC (Production)")
+    parser.add_argument('--load-data', type=str, required=True, help="Path to input CSV (LoadData format)")
+    parser.add_argument('--data-path', type=str, required=True, help="Base path for image files")
+    parser.add_argument('--illum-path', type=str, default=None, help="Folder containing .npy illumination functions")
+    parser.add_argument('--channels', nargs='+', required=True, help="List of channel names (e.g. CL488 CL568)")
+    parser.add_argument('--output', type=str, default='QC_Results.csv', help="Path for output CSV")
+    parser.add_argument('--threads', type=int, default=24, help="Number of threads for parallel processing")
+    return parser.parse_args(argv)
+
+
+_streams = threading.local()
+
+
+def _stream():
+    """One CUDA stream per worker thread (process_site is called from a thread pool, :212)."""
+    import torch
+    s = getattr(_streams, "s", None)
+    if s is None:
+        s = _streams.s = torch.cuda.Stream()
+    return s
+
+
+def _to_device_f64(image):
+    import torch
+    if isinstance(image, torch.Tensor):
+        return image.to(device="cuda", dtype=torch.float64)
+    return torch.from_numpy(np.ascontiguousarray(image, dtype=np.float64)).cuda()
+
+
+def rps(img):
+    """Radial power spectrum ring sums, Illumination_QC_mult.py:31-70.
+    Returns (labels, magsum, powersum) as NumPy arrays, or the reference's degenerate
+    ``[2], [0], [0]`` lists when min(H, W) < 24 (no ring to sum, :70)."""
+    import torch
+    from .. import ops
+    x = _to_device_f64(img)
+    assert x.dim() == 2
+    H, W = x.shape
+    maxwidth = min(H, W) / 8.0
+    if float(x.max() - x.min()) > 0:                         # np.ptp(img) > 0  (:52)
+        dev_abs = (x - x.mean()).abs().flatten()
+        x = x / torch.quantile(dev_abs, 0.5, interpolation="midpoint")   # np.median
+    spec = torch.fft.fft2(x - x.mean())                      # unshifted, DC removed (:57)
+    labels = np.arange(2, np.floor(maxwidth)).astype(int)
+    if len(labels) == 0:
+        return [2], [0], [0]
+    mag, pw = ops.ring_sums(spec[None].contiguous(), len(labels))
+    return labels, mag[0].cpu().numpy(), pw[0].cpu().numpy()
+
+
+def calculate_saturation_cp_exact(image, mask=None):
+    """PercentMaximal, Illumination_QC_mult.py:73-95: 100 * #(x == max x) / #x."""
+    import torch
+    x = _to_device_f64(image)
+    if mask is not None:
+        x = x[torch.as_tensor(mask, device=x.device)]
+    n = x.numel()
+    if n == 0:
+        return 0.0
+    return 100.0 * float((x == x.max()).sum().item()) / float(n)
+
+
+def _slope(radii, powersum):
+    import scipy.stats
+    valid = powersum > 0                                     # TypeError for the list case -> NaN
+    if np.sum(valid) > 2:
+        return scipy.stats.linregress(np.log(radii[valid]), np.log(powersum[valid]))[0]
+    return 0.0
+
+
+def calculate_qc_metrics(image, channel_name):
+    """Both metrics of one channel, :98-125 (a failing metric becomes NaN)."""
+    results = {}
+    try:
+        radii, _, powersum = rps(image)
+        results[f'ImageQuality_PowerLogLogSlope_{channel_name}'] = _slope(radii, powersum)
+    except Exception:
+        results[f'ImageQuality_PowerLogLogSlope_{channel_name}'] = np.nan
+    try:
+        results[f'ImageQuality_PercentMaximal_{channel_name}'] = calculate_saturation_cp_exact(image)
+    except Exception:
+        results[f'ImageQuality_PercentMaximal_{channel_name}'] = np.nan
+    return results
+
+
+def _corrected_and_pct(img_u16, illum):
+    """(float64 corrected image on the device, PercentMaximal).  When the illumination
+    function is float32-exact the fused kernel computes the divide-side PercentMaximal."""
+    import torch
+    from .. import ops
+    raw = torch.from_numpy(np.ascontiguousarray(img_u16)).cuda()
+    if illum is None or img_u16.shape != illum.shape:        # silently uncorrected (:148-153)
+        r = ops.preprocess_fused(raw[None, None, None], None, bin=1, want_maxproj=False, want_binned=False,
+                                 want_pct_maximal=True)
+        return raw.to(torch.float64), float(r["pct_maximal"][0, 0].item())
+    ill64 = np.ascontiguousarray(illum, dtype=np.float64)
+    ill32 = ill64.astype(np.float32)
+    d64 = torch.from_numpy(ill64).cuda()
+    corrected = raw.to(torch.float64) / d64
+    if np.array_equal(ill32.astype(np.float64), ill64):
+        r = ops.preprocess_fused(raw[None, None, None], torch.from_numpy(ill32[None]).cuda(), bin=1,
+                                 want_maxproj=False, want_binned=False, want_pct_maximal=True)
+        return corrected, float(r["pct_maximal"][0, 0].item())
+    return corrected, calculate_saturation_cp_exact(corrected)
+
+
+def process_site(site_data):
+    """One CSV row: (index, paths, channels, illum_cache) -> (index, {column: value}).
+    Never raises; see Illumination_QC_mult.py:131-162."""
+    import torch
+    index, paths, channels, illum_cache = site_data
+    site_results = {}
+    with torch.cuda.stream(_stream()):
+        for i, (path, ch_name) in enumerate(zip(paths, channels)):
+            try:
+                if not os.path.exists(path):
+                    site_results[f"QC_Error_{ch_name}"] = "File Not Found"
+                    continue
+                img = tiffio.read(path)
+                illum = illum_cache[i] if illum_cache and illum_cache[i] is not None else None
+                if img.dtype == np.uint16 and img.ndim == 2:
+                    corrected, pct = _corrected_and_pct(img, illum)
+                    try:
+                        radii, _, powersum = rps(corrected)
+                        site_results[f'ImageQuality_PowerLogLogSlope_{ch_name}'] = _slope(radii, powersum)
+                    except Exception:
+                        site_results[f'ImageQuality_PowerLogLogSlope_{ch_name}'] = np.nan
+                    site_results[f'ImageQuality_PercentMaximal_{ch_name}'] = pct
+                else:
+                    x = img.astype(float)
+                    if illum is not None and x.shape == illum.shape:
+                        x = x / illum
+                    site_results.update(calculate_qc_metrics(x, ch_name))
+            except Exception as e:
+                site_results[f"QC_Error_{ch_name}"] = str(e)
+        torch.cuda.current_stream().synchronize()
+    return index, site_results
+
+
+def load_illum_cache(illum_path, channels):
+    """{ch}_illum.npy, else Illum{ch}.npy, else None (:182-199)."""
+    cache = []
+    if not illum_path:
+        return [None] * len(channels)
+    for c in channels:
+        p1 = os.path.join(illum_path, f"{c}_illum.npy")
+        p2 = os.path.join(illum_path, f"Illum{c}.npy")
+        if os.path.exists(p1):
+            cache.append(np.load(p1))
+            logging.info(f"  Loaded {c}_illum.npy")
+        elif os.path.exists(p2):
+            cache.append(np.load(p2))
+            logging.info(f"  Loaded Illum{c}.npy")
+        else:
+            cache.append(None)
+            logging.warning(f"  Warning: No illumination file found for {c}")
+    return cache
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    logging.basicConfig(level=logging.INFO, format='%(asctime)s - %(message)s')
+    df = pd.read_csv(args.load_data)
+    cols_to_drop = [c for c in df.columns if 'ImageQuality_' in c or 'QC_Error' in c]
+    if cols_to_drop:
+        df = df.drop(columns=cols_to_drop)
+    channel_cols = [f'FileName_{c}' for c in args.channels]
+    illum_cache = load_illum_cache(args.illum_path, args.channels)
+    tasks = []
+    for idx, row in df.iterrows():
+        paths = [os.path.join(args.data_path, row[col]) for col in channel_cols]
+        tasks.append((idx, paths, args.channels, illum_cache))
+    logging.info(f"Starting processing on {len(tasks)} sites with {args.threads} threads...")
+    results_dict = {}
+    with concurrent.futures.ThreadPoolExecutor(max_workers=args.threads) as executor:
+        futures = {executor.submit(process_site, t): t[0] for t in tasks}
+        for future in concurrent.futures.as_completed(futures):
+            idx, res = future.result()
+            results_dict[idx] = res
+    qc_df = pd.DataFrame.from_dict(results_dict, orient='index').sort_index()
+    final_df = pd.concat([df, qc_df], axis=1)
+    final_df.to_csv(args.output, index=False)
+    logging.info(f"Done! Saved to {args.output}")
+    return final_df
+
+
+if __name__ == '__main__':
+    main()

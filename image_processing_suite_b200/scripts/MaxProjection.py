@@ -1,0 +1,127 @@
+"""Drop-in for MaxProjection.py: same functions, same flags, same output keys; the
+elementwise z-max (MaxProjection.py:45) runs in ips_preprocess_fused on the GPU.
+
+``max_projection`` keeps the reference's per-group contract.  ``max_project_chunk`` is what
+the CLI loop uses: all channels of one field (C x Z planes) in a single fused launch.
+"""
+import argparse
+import csv
+import io
+import logging
+import posixpath
+from io import StringIO
+
+import numpy as np
+import pandas as pd
+
+from . import storage, tiffio
+
+logging.basicConfig(level=logging.INFO)
+logger = logging.getLogger(__name__)
+
+
+def modify_imagepath(filepath):
+    """'Images' path component -> 'ImagesStacked' (MaxProjection.py:16-22)."""
+    parts = filepath.split('/')
+    if 'Images' not in parts:
+        return filepath
+    parts[parts.index('Images')] = 'ImagesStacked'
+    return '/'.join(parts)
+
+
+def read_csv_from_s3(bucket_name, file_key, s3_client=None):
+    """Data-set CSV with ';' or ',' sniffed from the first KiB (MaxProjection.py:24-31)."""
+    s3 = s3_client or storage.client()
+    content = s3.get_object(Bucket=bucket_name, Key=file_key)['Body'].read().decode('utf-8')
+    dialect = csv.Sniffer().sniff(content[:1024], delimiters=";,")
+    return pd.read_csv(StringIO(content), sep=dialect.delimiter)
+
+
+def _fetch(image_key, bucket_name, s3_client):
+    return tiffio.decode(s3_client.get_object(Bucket=bucket_name, Key=image_key)['Body'].read())
+
+
+def _project(stack_czhw):
+    """[C][Z][H][W] uint16 (host) -> [C][H][W] uint16 via the CUDA kernel."""
+    import torch
+    from .. import ops
+    raw = torch.from_numpy(np.ascontiguousarray(stack_czhw[None])).cuda()
+    return ops.preprocess_fused(raw, None, bin=1, want_binned=False)["maxproj"][0].cpu().numpy()
+
+
+def max_projection(image_group, bucket_name, s3_client):
+    """Max-project the planes of one channel and upload the result (MaxProjection.py:33-52).
+    Raises ValueError when the planes differ in shape, like the reference (:42-43)."""
+    images = [_fetch(k, bucket_name, s3_client) for k in image_group]
+    if not all(img.shape == images[0].shape for img in images):
+        raise ValueError(f"Image shape mismatch in group: {image_group}")
+    if images[0].dtype != np.uint16:
+        raise ValueError("max_projection expects 16-bit images, got %s" % images[0].dtype)
+    max_proj = _project(np.stack(images)[None])[0]
+    s3_client.upload_fileobj(io.BytesIO(tiffio.encode(max_proj)), bucket_name, modify_imagepath(image_group[0]))
+
+
+def max_project_chunk(groups, bucket_name, s3_client):
+    """groups: list over channels of lists over planes of keys.  One launch for the field;
+    channels whose planes fail to load or mismatch are reported like the reference does
+    (logged, the other channels still go through).  Returns the number written."""
+    stacks, ok = [], []
+    for j, group in enumerate(groups):
+        try:
+            images = [_fetch(k, bucket_name, s3_client) for k in group]
+            if not all(img.shape == images[0].shape for img in images):
+                raise ValueError(f"Image shape mismatch in group: {group}")
+            stacks.append(np.stack(images))
+            ok.append(j)
+        except Exception as e:
+            logger.error(f"Error processing group {j}: {e}")
+    written = 0
+    by_shape = {}
+    for j, st in zip(ok, stacks):
+        by_shape.setdefault(st.shape, []).append((j, st))
+    for items in by_shape.values():
+        proj = _project(np.stack([st for _, st in items]))
+        for (j, _), mp in zip(items, proj):
+            s3_client.upload_fileobj(io.BytesIO(tiffio.encode(mp)), bucket_name, modify_imagepath(groups[j][0]))
+            written += 1
+    return written
+
+
+def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_client=None):
+    """The CLI loop of MaxProjection.py:64-95: plates, chunks of C*Z rows (plane-major,
+    channel-minor: channel j, plane p is row j + p*C), incomplete tail chunks skipped."""
+    s3_client = s3_client or storage.client()
+    group_size = num_channels * num_planes
+    df = read_csv_from_s3(bucket_data_set, data_set, s3_client)
+    total = 0
+    for plate in df['PlateID'].unique():
+        sub = df[df['PlateID'] == plate]
+        for i in range(0, len(sub), group_size):
+            chunk = sub.iloc[i: i + group_size]
+            if len(chunk) < group_size:
+                logger.warning(f"Skipping incomplete chunk in plate {plate} at index {i}")
+                continue
+            groups = [[posixpath.join(chunk.iloc[j + p * num_channels].Image_PathName,
+                                      chunk.iloc[j + p * num_channels].Image_FileName)
+                       for p in range(num_planes)] for j in range(num_channels)]
+            total += max_project_chunk(groups, bucket_images, s3_client)
+        logger.info(f"Plate {plate} finished! Check images in bucket.")
+    return total
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="Process image plates using ImageJ and upload results to S3.")
+    parser.add_argument("--bucket_data_set", type=str, required=True, help="S3 bucket containing the data set.")
+    parser.add_argument("--data_set", type=str, required=True,
+                        help="Data set key location containing per PlateID images to process containing 'ChannelName', "
+                             "'ChannelID', 'Image_FileName', 'Image_PathName', 'FieldID', 'PlaneID', 'PlateID', 'Row', "
+                             "'Col', 'Timestamp'.")
+    parser.add_argument("--channels", type=int, required=True, help="Number of channels per group")
+    parser.add_argument("--planes", type=int, required=True, help="Number of planes per channel")
+    parser.add_argument("--bucket_images", type=str, required=True, help="S3 bucket containing the raw images to max project.")
+    return parser
+
+
+if __name__ == "__main__":
+    a = build_parser().parse_args()
+    run(a.bucket_data_set, a.data_set, a.channels, a.planes, a.bucket_images)

@@ -1,0 +1,98 @@
+"""The handful of S3 calls the reference scripts make, over boto3 or a local directory.
+
+Reference call sites: get_object / upload_fileobj (MaxProjection.py:24-27, :36-37, :52),
+bucket.objects.filter / obj.get / bucket.put_object (Image_re-binning.py:41-55).
+"""
+import io
+import os
+
+
+class _Body:
+    def __init__(self, data):
+        self._data = data
+
+    def read(self):
+        return self._data
+
+
+class LocalObject:
+    def __init__(self, root, bucket, key):
+        self._root, self._bucket, self.key = root, bucket, key
+
+    def get(self):
+        with open(os.path.join(self._root, self._bucket, self.key), "rb") as f:
+            return {"Body": _Body(f.read())}
+
+
+class _LocalObjects:
+    def __init__(self, root, bucket):
+        self._root, self._bucket = root, bucket
+
+    def filter(self, Prefix=""):
+        base = os.path.join(self._root, self._bucket)
+        out = []
+        for d, _, files in os.walk(base):
+            for name in files:
+                key = os.path.relpath(os.path.join(d, name), base).replace(os.sep, "/")
+                if key.startswith(Prefix):
+                    out.append(LocalObject(self._root, self._bucket, key))
+        return sorted(out, key=lambda o: o.key)
+
+
+class LocalBucket:
+    def __init__(self, root, name):
+        self._root, self.name = root, name
+        self.objects = _LocalObjects(root, name)
+
+    def put_object(self, Key, Body, ContentType=None):
+        path = os.path.join(self._root, self.name, Key)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            f.write(Body)
+
+
+class LocalClient:
+    """Subset of boto3's S3 client + resource over ``root/<bucket>/<key>``."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def get_object(self, Bucket, Key):
+        path = os.path.join(self.root, Bucket, Key)
+        if not os.path.exists(path):
+            raise FileNotFoundError("no such key: s3://%s/%s" % (Bucket, Key))
+        with open(path, "rb") as f:
+            return {"Body": _Body(f.read())}
+
+    def upload_fileobj(self, fileobj, Bucket, Key):
+        path = os.path.join(self.root, Bucket, Key)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            f.write(fileobj.read())
+
+    def put_object(self, Bucket, Key, Body, ContentType=None):
+        self.upload_fileobj(io.BytesIO(Body), Bucket, Key)
+
+    def Bucket(self, name):
+        return LocalBucket(self.root, name)
+
+
+def local_root():
+    return os.environ.get("IPS_STORAGE_ROOT")
+
+
+def client():
+    """boto3.client('s3') unless IPS_STORAGE_ROOT selects the directory-backed stand-in."""
+    root = local_root()
+    if root:
+        return LocalClient(root)
+    import boto3
+    return boto3.client("s3")
+
+
+def resource():
+    root = local_root()
+    if root:
+        return LocalClient(root)
+    import boto3
+    return boto3.resource("s3")

@@ -1,0 +1,160 @@
+"""Drop-in scripts end to end on a local directory (IPS_STORAGE_ROOT), CUDA path vs the
+oracle and vs the golden fixtures made by the reference's own functions."""
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from image_processing_suite_b200 import synth
+from oracle import illum as o_illum
+from oracle import lanczos as o_lz
+from oracle import object_stats as o_obj
+from oracle import preprocess as o_pre
+from oracle import qc as o_qc
+from tests.gpu_util import require_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def test_max_projection_script(tmp_path, monkeypatch):
+    require_gpu()
+    from image_processing_suite_b200.scripts import MaxProjection, storage, tiffio
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    s3 = storage.client()
+    C, Z, H, W = 2, 3, 40, 56
+    rng = np.random.default_rng(1)
+    rows, stacks = [], {}
+    for field in range(2):
+        st = rng.integers(0, 65536, (C, Z, H, W), dtype=np.uint16)
+        stacks[field] = st
+        for p in range(Z):                                   # plane-major, channel-minor rows
+            for j in range(C):
+                name = f"f{field}p{p}c{j}.tiff"
+                s3.upload_fileobj(io.BytesIO(tiffio.encode(st[j, p])), "img", f"exp/Images/{name}")
+                rows.append({"PlateID": "P1", "Image_PathName": "exp/Images", "Image_FileName": name})
+    rows.append({"PlateID": "P1", "Image_PathName": "exp/Images", "Image_FileName": "tail.tiff"})   # incomplete chunk
+    csv_bytes = pd.DataFrame(rows).to_csv(index=False, sep=";").encode()
+    s3.upload_fileobj(io.BytesIO(csv_bytes), "sets", "d.csv")
+    n = MaxProjection.run("sets", "d.csv", C, Z, "img", s3)
+    assert n == 4
+    for field in range(2):
+        for j in range(C):
+            out = tiffio.decode(s3.get_object(Bucket="img", Key=f"exp/ImagesStacked/f{field}p0c{j}.tiff")["Body"].read())
+            np.testing.assert_array_equal(out, o_pre.max_projection(list(stacks[field][j])))
+    # the per-group function with the reference's error contract
+    with pytest.raises(FileNotFoundError):
+        MaxProjection.max_projection(["exp/Images/missing.tiff"], "img", s3)
+    s3.upload_fileobj(io.BytesIO(tiffio.encode(np.zeros((8, 9), np.uint16))), "img", "exp/Images/odd.tiff")
+    with pytest.raises(ValueError, match="shape mismatch"):
+        MaxProjection.max_projection(["exp/Images/f0p0c0.tiff", "exp/Images/odd.tiff"], "img", s3)
+
+
+def test_rebinning_script(tmp_path, monkeypatch, golden_dir):
+    require_gpu()
+    from image_processing_suite_b200.scripts import Image_rebinning, storage, tiffio
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    g = np.load(os.path.join(golden_dir, "rebin_lanczos.npz"))
+    src = g["x2_in"]
+    out = tiffio.decode(Image_rebinning.process_image_in_memory(tiffio.encode(src), (src.shape[1] // 2, src.shape[0] // 2)))
+    np.testing.assert_array_equal(out, g["x2_out"])
+    s3 = storage.client()
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 65536, (120, 120), dtype=np.uint16)
+    s3.put_object(Bucket="b", Key="e/Image/a.tiff", Body=tiffio.encode(img))
+    s3.put_object(Bucket="b", Key="e/Image/notes.txt", Body=b"skip me")
+    s3.put_object(Bucket="b", Key="e/Image/bad.tiff", Body=b"not a tiff")
+    assert Image_rebinning.process_images_in_s3("b", "e/Image", 60) == 1      # bad file logged and skipped
+    got = tiffio.decode(s3.get_object(Bucket="b", Key="e/Image_binned/a.tiff")["Body"].read())
+    np.testing.assert_array_equal(got, o_lz.pil_resize(img, (60, 60)))
+
+
+def test_illumination_qc_script(tmp_path, golden_dir):
+    require_gpu()
+    from image_processing_suite_b200.scripts import Illumination_QC_mult as qc, tiffio
+    g = np.load(os.path.join(golden_dir, "illum_qc.npz"))
+    # reference-function goldens: slope and PercentMaximal of corrected images
+    os.makedirs(tmp_path / "img")
+    os.makedirs(tmp_path / "illum")
+    rows = []
+    for case in ("a", "b", "c"):
+        tiffio.write(str(tmp_path / "img" / f"{case}.tiff"), g[f"{case}_img"])
+        rows.append({"FileName_CH1": f"{case}.tiff", "Metadata_Well": case})
+    rows.append({"FileName_CH1": "missing.tiff", "Metadata_Well": "z"})
+    # one illumination function per channel: use case a's; b and c have other shapes or the same
+    np.save(tmp_path / "illum" / "CH1_illum.npy", g["a_illum"])
+    pd.DataFrame(rows).to_csv(tmp_path / "load.csv", index=False)
+    out = qc.main(["--load-data", str(tmp_path / "load.csv"), "--data-path", str(tmp_path / "img"),
+                   "--illum-path", str(tmp_path / "illum"), "--channels", "CH1",
+                   "--output", str(tmp_path / "qc.csv"), "--threads", "3"])
+    assert out.loc[3, "QC_Error_CH1"] == "File Not Found"
+    ref_a_slope, ref_a_pct = float(g["a_slope_corr"]), float(g["a_pct_corr"])
+    assert out.loc[0, "ImageQuality_PowerLogLogSlope_CH1"] == pytest.approx(ref_a_slope, rel=1e-6)
+    assert out.loc[0, "ImageQuality_PercentMaximal_CH1"] == ref_a_pct
+    for k, case in ((1, "b"), (2, "c")):
+        img, ill = g[f"{case}_img"], g["a_illum"]
+        corr = o_pre.illum_correct(img, ill)                 # shape mismatch -> uncorrected
+        assert out.loc[k, "ImageQuality_PowerLogLogSlope_CH1"] == pytest.approx(o_qc.power_loglog_slope(corr), rel=1e-6)
+        assert out.loc[k, "ImageQuality_PercentMaximal_CH1"] == o_qc.percent_maximal(corr)
+    # degenerate cases of the reference
+    assert qc.calculate_qc_metrics(np.full((48, 48), 7.0), "X") == {
+        "ImageQuality_PowerLogLogSlope_X": 0.0, "ImageQuality_PercentMaximal_X": 100.0}
+    assert np.isnan(qc.calculate_qc_metrics(np.random.default_rng(0).random((20, 30)), "X")["ImageQuality_PowerLogLogSlope_X"])
+    saved = pd.read_csv(tmp_path / "qc.csv")
+    assert "ImageQuality_PercentMaximal_CH1" in saved.columns and len(saved) == 4
+
+
+def test_feature_extraction_and_illum_estimate_scripts(tmp_path):
+    require_gpu()
+    from image_processing_suite_b200.scripts import Feature_extraction as fe, Illumination_estimate as ie, tiffio
+    C, H, W, cells, sites = 2, 96, 128, 10, 5
+    chans = ["DNA", "ER"]
+    os.makedirs(tmp_path / "img")
+    rows, labs, mps = [], [], []
+    for s in range(sites):
+        lab = synth.make_labels(H, W, cells, seed=s, amin=5, amax=10)
+        mp = o_pre.max_projection_field(synth.field_numpy(lab, c=C, z=2, seed=s))
+        labs.append(lab); mps.append(mp)
+        row = {"Metadata_Well": f"A{s // 2 + 1:02d}", "Metadata_Site": s % 2 + 1}
+        for j, ch in enumerate(chans):
+            tiffio.write(str(tmp_path / "img" / f"s{s}_{ch}.tiff"), mp[j])
+            row[f"FileName_{ch}"] = f"s{s}_{ch}.tiff"
+            row[f"PathName_{ch}"] = str(tmp_path / "img")
+        tiffio.write(str(tmp_path / "img" / f"s{s}_mask.tiff"), lab.astype(np.uint16))
+        row["Objects_FileName_Nuclei"] = f"s{s}_mask.tiff"
+        row["Objects_PathName_Nuclei"] = str(tmp_path / "img")
+        rows.append(row)
+    pd.DataFrame(rows).to_csv(tmp_path / "load.csv", index=False)
+    # 1. estimate illumination functions for the "plate"
+    funcs = ie.main(["--load-data", str(tmp_path / "load.csv"), "--data-path", str(tmp_path / "img"),
+                     "--illum-path", str(tmp_path / "illum"), "--channels", *chans, "--filter-size", "20", "--batch", "2"])
+    ref = o_illum.estimate(np.stack(mps), 20 / 2.35, 0.02)
+    for j, ch in enumerate(chans):
+        np.testing.assert_allclose(funcs[ch], ref[j], rtol=1e-5)
+        assert np.load(tmp_path / "illum" / f"{ch}_illum.npy").dtype == np.float32
+    # 2. add them to the LoadData CSV (load_data_*_illum.csv) and run the CellProfiler-style CLI
+    df = pd.read_csv(tmp_path / "load.csv")
+    for ch in chans:
+        df[f"FileName_Illum{ch}"] = f"{ch}_illum.npy"
+        df[f"PathName_Illum{ch}"] = str(tmp_path / "illum")
+    df.to_csv(tmp_path / "load_illum.csv", index=False)
+    fe.main(["-c", "-r", "-p", "Feature_Extraction_CL2.0.cppipe", "-o", str(tmp_path / "out"),
+             "--data-file", str(tmp_path / "load_illum.csv"), "--batch", "2"])
+    image = pd.read_csv(tmp_path / "out" / "Image.csv")
+    nuclei = pd.read_csv(tmp_path / "out" / "Nuclei.csv")
+    assert list(image.ImageNumber) == [1, 2, 3, 4, 5] and "Metadata_Well" in image.columns
+    assert str(nuclei.AreaShape_Area.dtype).startswith("int") and str(image.Count_Nuclei.dtype).startswith("int")
+    ill = np.stack([funcs[ch] for ch in chans])
+    for s in range(sites):
+        e_i, e_f = o_obj.object_stats(labs[s], mps[s], ill, 1 / 65535.0)
+        sub = nuclei[nuclei.ImageNumber == s + 1]
+        assert int(image.Count_Nuclei[s]) == e_i.shape[0] == len(sub)
+        np.testing.assert_array_equal(sub.ObjectNumber, e_i[:, 0])
+        np.testing.assert_array_equal(sub.AreaShape_Area, e_i[:, 1])
+        np.testing.assert_array_equal(sub.AreaShape_BoundingBoxMinimum_Y, e_i[:, 2])
+        np.testing.assert_array_equal(sub.AreaShape_BoundingBoxMaximum_X, e_i[:, 5])
+        np.testing.assert_allclose(sub.Location_Center_X, e_f[:, 1], rtol=1e-5)
+        np.testing.assert_allclose(sub.Intensity_MeanIntensity_ER, e_f[:, 2 + 5 + 1], rtol=1e-5)
+        np.testing.assert_allclose(sub.Intensity_StdIntensity_DNA, e_f[:, 2 + 2], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(sub.Intensity_IntegratedIntensity_DNA, e_f[:, 2 + 0], rtol=1e-5)
