@@ -270,24 +270,55 @@ def gpu_arm(args):
 
     nb = R // Fb
     fused = args.mode == "fused"
+    # object rows of the whole plate shard stay resident (they are what the all-gather moves):
+    # step i writes the rows of its 16 fields into its own slice
+    n_plate = min(args.steps, max(1, 4096 // Fb)) * Fb
+    plate_n = torch.zeros((n_plate,), dtype=torch.int32, device=dev)
+    plate_ints = torch.zeros((n_plate, n_max, 6), dtype=torch.int32, device=dev)
+    plate_flts = torch.zeros((n_plate, n_max, 2 + 5 * C_), dtype=torch.float32, device=dev)
+    n_slots = n_plate // Fb
+    # field -> well: 9 sites per well, wells dealt round-robin over ranks (plate.shard_wells)
+    sites = 9
+    n_wells_local = (n_plate + sites - 1) // sites
+    field_well = (torch.arange(n_plate, device=dev, dtype=torch.int32) // sites) * world + rank
+    n_wells = n_wells_local * world
+    ws_f = None
     k1_out = [None] * nb
-    k3_out = [None] * nb
-    for b in range(nb):                                   # preallocate every output once
+    for b in range(nb):                                   # preallocate the image outputs once
         sl = slice(b * Fb, (b + 1) * Fb)
+        rows0 = {"n_objects": plate_n[:Fb], "ints": plate_ints[:Fb], "flts": plate_flts[:Fb]}
         if fused:
-            k1_out[b] = ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max)
+            k1_out[b] = ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max, out=rows0)
+            ws_f = k1_out[b]["ws"]
         else:
             k1_out[b] = ops.preprocess_fused(raw[sl], illum, bin=BIN)
-            k3_out[b] = ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max)
+            ws_f = ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=rows0)["ws"]
     torch.cuda.synchronize()
+    from image_processing_suite_b200 import plate as plate_mod
+    D_row = 10 + 5 * C_
+    rows_buf = torch.empty((n_plate * n_max, D_row), dtype=torch.float32, device=dev)
+    gatherer = plate_mod.RowGatherer(n_plate * n_max, D_row) if world > 1 else None
+
+    def aggregate():
+        """End of the plate shard: dense rows -> the one all-gather -> per-well means."""
+        rows, total = plate_mod.pack_rows(plate_ints, plate_flts, plate_n, field_well, out=rows_buf)
+        if gatherer is None:
+            res = plate_mod.well_means(rows.view(1, n_plate * n_max, D_row), total.view(1), n_wells)
+            return res, int(total.item())
+        n = int(total.item())
+        all_rows, counts = gatherer.gather(rows, n)
+        return plate_mod.well_means(all_rows, counts, n_wells), n
 
     def step(i, ev=None):
         b = i % nb
         sl = slice(b * Fb, (b + 1) * Fb)
+        ps = slice((i % n_slots) * Fb, (i % n_slots + 1) * Fb)
+        rows_out = {"n_objects": plate_n[ps], "ints": plate_ints[ps], "flts": plate_flts[ps], "ws": ws_f}
         if ev is not None:
             ev[0].record()
         if fused:
-            ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max, out=k1_out[b])
+            ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max,
+                            out={"maxproj": k1_out[b]["maxproj"], "binned": k1_out[b]["binned"], **rows_out})
             if ev is not None:
                 ev[1].record()
                 ev[2].record()
@@ -295,12 +326,13 @@ def gpu_arm(args):
         ops.preprocess_fused(raw[sl], illum, bin=BIN, out=k1_out[b])
         if ev is not None:
             ev[1].record()
-        ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=k3_out[b])
+        ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=rows_out)
         if ev is not None:
             ev[2].record()
 
     for i in range(args.warmup):
         step(i)
+    aggregate()                                             # warm the gather / aggregation path too
     torch.cuda.synchronize()
 
     def barrier():
@@ -310,16 +342,20 @@ def gpu_arm(args):
 
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_steps = torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = capi.launch_count()
     with ClockSampler(local) as clocks:
         t_begin.record()
         for i in range(args.steps):
-            step(args.warmup + i, evs[i])
+            step(i, evs[i])
+        t_steps.record()
+        (well_mean_dev, well_count_dev), n_rows = aggregate()
         t_end.record()
         barrier()
     launches = capi.launch_count() - l0
     ms_total = t_begin.elapsed_time(t_end)
+    ms_aggregate = t_steps.elapsed_time(t_end)
     k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     k3_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     if dist is not None:
@@ -427,6 +463,11 @@ def gpu_arm(args):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": per_field[dom] * Fb + ill_b},
             "kernels": kernels,
+            "aggregation": {"what": "pack rows -> %s -> per-well mean, once per plate shard, inside the timed region" % (
+                                "one NCCL all-gather (ips_allgather_rows)" if world > 1 else "no gather at N=1"),
+                            "ms": ms_aggregate, "rows_per_rank": n_rows, "row_bytes": D_row * 4,
+                            "gather_bytes_per_rank": n_rows * D_row * 4 if world > 1 else 0,
+                            "wells": n_wells, "wells_with_rows": int((well_count_dev > 0).sum().item())},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "objects_last_field": int(n_obj_last[-1]),

@@ -1,0 +1,157 @@
+"""Plate-level host logic: sharding fields over ranks, dense object rows, the one all-gather
+and the well aggregation that follows it (north_star).
+
+Sharding: fields are independent units; all sites of a well go to one rank
+(``rank = well_index mod world``), so the per-field path needs no communication.  After the
+last field of a plate-timepoint each rank packs its object rows (``pack_rows``), the ranks
+exchange them with ONE all-gather (``RowGatherer``: NCCL through libips.so on GPUs; the same
+padded-block protocol over ``torch.distributed`` for the gloo tests), and every rank computes
+the per-well means (``well_means``) that Normalize_CP_ami.py:126 computes with pandas.
+"""
+import ctypes as C
+
+import torch
+
+from . import capi
+
+ROW_PREFIX = ("well", "field", "label", "area", "y0", "x0", "y1", "x1", "cy", "cx")
+
+
+def row_columns(channels):
+    cols = list(ROW_PREFIX)
+    for ch in channels:
+        cols += [f"sum_{ch}", f"mean_{ch}", f"std_{ch}", f"min_{ch}", f"max_{ch}"]
+    return cols
+
+
+def well_name(index, n_cols=24):
+    """0-based well index -> 'A01' ... 'P24' (384-well plate: 16 rows x 24 columns)."""
+    r, c = divmod(int(index), n_cols)
+    return "%s%02d" % (chr(ord("A") + r), c + 1)
+
+
+def shard_wells(n_wells, rank, world):
+    """Wells owned by ``rank``: every ``world``-th well (balanced to within one well)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world %d" % (rank, world))
+    return list(range(rank, n_wells, world))
+
+
+def plate_fields(n_wells, sites_per_well, rank=0, world=1):
+    """(well, site) pairs of the rank's shard, wells ascending, sites 1..n inside a well."""
+    return [(w, s) for w in shard_wells(n_wells, rank, world) for s in range(1, sites_per_well + 1)]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def pack_rows(ints, flts, n_objects, field_well, field_base=0, out=None):
+    """Padded per-field outputs -> dense float32 rows [total][10 + 5C] (device).
+
+    Returns (rows buffer [F * Nmax][D], total as a 0-d int64 device tensor).  Only the first
+    ``total`` rows are valid.  ``field_well`` [F] int32 = well index of each field.
+    """
+    F, n_max, _ = ints.shape
+    nf = flts.shape[2]
+    Cn = (nf - 2) // 5
+    dev = ints.device
+    if not (ints.is_cuda and flts.is_cuda and n_objects.is_cuda and field_well.is_cuda):
+        raise ValueError("pack_rows works on device tensors (there is no CPU path)")
+    if field_well.dtype != torch.int32 or field_well.shape[0] != F:
+        raise ValueError("field_well must be int32 [F]")
+    with torch.cuda.device(dev):
+        rows = out if out is not None else torch.empty((F * n_max, 8 + nf), dtype=torch.float32, device=dev)
+        total = torch.zeros((), dtype=torch.int64, device=dev)
+        ws = torch.empty(max(int(capi.call("ips_pack_rows_workspace_bytes", F)), 16), dtype=torch.uint8, device=dev)
+        capi.call("ips_pack_rows", _ptr(ints), _ptr(flts), _ptr(n_objects), _ptr(field_well), int(field_base),
+                  _ptr(rows), _ptr(total), n_max, Cn, F, _ptr(ws), ws.numel(), _stream(dev))
+    return rows, total
+
+
+class RowGatherer:
+    """The one collective: every rank contributes ``n_local`` rows of ``D`` float32, every rank
+    receives all of them as a padded table [world][cap][D] plus the per-rank counts.
+
+    backend "ips": ncclAllGather inside libips.so (its own communicator; the unique id travels
+    over the caller's torch.distributed group).  backend "torch": the same protocol with
+    torch.distributed collectives on whatever device the tensors live on (used by the
+    world_size-2 gloo tests; not a product path on GPUs).
+    """
+
+    def __init__(self, cap_per_rank, D, group=None, backend=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cap, self.D = int(cap_per_rank), int(D)
+        self.backend = backend or ("ips" if torch.cuda.is_available() else "torch")
+        self._comm = None
+        if self.backend == "ips" and self.world > 1:
+            n = int(capi.call("ips_comm_unique_id_bytes"))
+            buf = (C.c_char * n)()
+            if self.rank == 0:
+                capi.call("ips_comm_unique_id", C.cast(buf, C.c_void_p), n)
+            box = [bytes(buf)]
+            dist.broadcast_object_list(box, src=0, group=group)
+            uid = (C.c_char * n).from_buffer_copy(box[0])
+            h = C.c_void_p()
+            capi.call("ips_comm_create", C.byref(h), C.cast(uid, C.c_void_p), n, self.rank, self.world)
+            self._comm = h
+
+    def gather(self, local_rows, n_local):
+        """local_rows [>= n_local][D] float32 -> (all_rows [world][cap][D], counts [world] int64)."""
+        n_local = int(n_local)
+        if n_local > self.cap:
+            raise ValueError("%d rows exceed the per-rank capacity %d" % (n_local, self.cap))
+        if local_rows.dtype != torch.float32 or local_rows.dim() != 2 or local_rows.shape[1] != self.D:
+            raise ValueError("rows must be float32 [n][%d]" % self.D)
+        dev = local_rows.device
+        all_rows = torch.empty((self.world, self.cap, self.D), dtype=torch.float32, device=dev)
+        counts = torch.zeros((self.world,), dtype=torch.int64, device=dev)
+        if self.world == 1:
+            all_rows[0, :n_local].copy_(local_rows[:n_local])
+            counts[0] = n_local
+            return all_rows, counts
+        if self.backend == "ips":
+            with torch.cuda.device(dev):
+                capi.call("ips_allgather_rows", self._comm, _ptr(local_rows), n_local, self.D * 4, _ptr(all_rows),
+                          _ptr(counts), self.cap, _stream(dev))
+            return all_rows, counts
+        mine = torch.zeros((self.cap, self.D), dtype=torch.float32, device=dev)
+        mine[:n_local].copy_(local_rows[:n_local])
+        self.dist.all_gather(list(counts.split(1)), torch.tensor([n_local], dtype=torch.int64, device=dev),
+                             group=self.group)
+        blocks = [all_rows[r] for r in range(self.world)]
+        self.dist.all_gather(blocks, mine, group=self.group)
+        return all_rows, counts
+
+    def close(self):
+        if self._comm is not None:
+            capi.call("ips_comm_destroy", self._comm)
+            self._comm = None
+
+
+def well_ids_of(all_rows, counts):
+    """int32 well id per row of a gathered table, -1 for padding."""
+    world, cap, D = all_rows.shape
+    dev = all_rows.device
+    if dev.type != "cuda":
+        idx = torch.arange(cap)[None, :] < counts[:, None]
+        return torch.where(idx, all_rows[:, :, 0].to(torch.int32), torch.full((), -1, dtype=torch.int32)).reshape(-1)
+    well = torch.empty((world * cap,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        capi.call("ips_rows_well_ids", _ptr(all_rows), _ptr(counts), _ptr(well), cap, world, D, _stream(dev))
+    return well
+
+
+def well_means(all_rows, counts, n_wells):
+    """Per-well mean of every row column (device): (mean [n_wells][D] float64, count [n_wells])."""
+    from . import ops
+    world, cap, D = all_rows.shape
+    return ops.well_mean(all_rows.reshape(world * cap, D), well_ids_of(all_rows, counts), n_wells)

@@ -174,6 +174,24 @@ size_t ips_well_mean_workspace_bytes(int n_wells, int D);
 int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
                   int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream);
 
+/* ---- dense object rows (what the all-gather moves and the well aggregation reads) ---------
+ * Compacts the padded per-field outputs of ips_object_stats / ips_field_fused into one
+ * float32 row per object, the table the reference's consumers read from Nuclei.csv /
+ * Cells.csv (Normalize_CP_ami.py:57-64):
+ *   [well, field, label, area, y0, x0, y1, x1, cy, cx, C x (sum, mean, std, min, max)]
+ * (D = 10 + 5C columns; integers are exact in float32).  field_well [F] int32 is the well id
+ * of each field, field = field_base + index.  Fields with n_objects < 0 contribute no rows.
+ * total_out (device int64) receives the number of rows.  F <= 65535.
+ */
+size_t ips_pack_rows_workspace_bytes(int F);
+int ips_pack_rows(const int32_t* ints, const float* flts, const int32_t* n_objects,
+                  const int32_t* field_well, int field_base, float* rows_out, int64_t* total_out,
+                  int Nmax, int C, int F, void* ws, size_t ws_bytes, ips_stream_t stream);
+/* Column 0 of a gathered [world][cap_per_rank][D] row table -> int32 well id per row, -1 for
+ * the padding behind each rank's count (ips_well_mean drops ids outside [0, n_wells)). */
+int ips_rows_well_ids(const float* rows, const int64_t* counts_dev, int32_t* well_out,
+                      int64_t cap_per_rank, int world, int D, ips_stream_t stream);
+
 /* ---- the one collective: all-gather of per-object rows ----------------------------------
  * north_star's "one NCCL all-gather of per-object feature rows for well-level aggregation
  * and normalisation" (the reference has no collective; parity target is the pandas groupby

@@ -1,0 +1,73 @@
+"""Host-side plate logic on the CPU: sharding, row schema, and the padded all-gather protocol
+over gloo with world_size 2 (the N > 1 path of bench.py / plate.py without GPUs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from image_processing_suite_b200 import plate
+
+
+def test_sharding_covers_every_well_once():
+    for world in (1, 2, 4, 8, 5):
+        seen = []
+        for r in range(world):
+            wells = plate.shard_wells(384, r, world)
+            assert len(wells) in (384 // world, 384 // world + 1)
+            seen += wells
+        assert sorted(seen) == list(range(384))
+    fields = plate.plate_fields(384, 9, rank=3, world=8)
+    assert len(fields) == 48 * 9 and fields[0] == (3, 1) and fields[9] == (11, 1)
+    with pytest.raises(ValueError):
+        plate.shard_wells(384, 8, 8)
+
+
+def test_well_names_and_row_schema():
+    assert plate.well_name(0) == "A01" and plate.well_name(23) == "A24" and plate.well_name(383) == "P24"
+    cols = plate.row_columns(["DNA", "ER"])
+    assert cols[:10] == list(plate.ROW_PREFIX) and len(cols) == 10 + 5 * 2 and cols[-1] == "max_ER"
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D, cap = 7, 20
+        rng = np.random.default_rng(100 + rank)
+        wells = plate.shard_wells(6, rank, world)
+        n_local = 5 + 4 * rank
+        rows = torch.from_numpy(rng.normal(size=(n_local, D)).astype(np.float32))
+        rows[:, 0] = torch.tensor([wells[i % len(wells)] for i in range(n_local)], dtype=torch.float32)
+        g = plate.RowGatherer(cap, D, backend="torch")
+        all_rows, counts = g.gather(rows, n_local)
+        assert counts.tolist() == [5 + 4 * r for r in range(world)]
+        assert torch.equal(all_rows[rank, :n_local], rows)
+        ids = plate.well_ids_of(all_rows, counts)
+        assert int((ids >= 0).sum()) == int(counts.sum())
+        # every rank ends up with the same table -> same per-well means as a pandas groupby
+        valid = ids >= 0
+        flat = all_rows.reshape(-1, D)[valid].numpy().astype(np.float64)
+        means = {int(w): flat[flat[:, 0] == w].mean(axis=0) for w in np.unique(flat[:, 0])}
+        torch.save({"means": means, "counts": counts}, os.path.join(tmp, f"r{rank}.pt"))
+        with pytest.raises(ValueError):
+            g.gather(torch.zeros((cap + 1, D)), cap + 1)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_gather_protocol_gloo_world2(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / "r0.pt", weights_only=False)
+    b = torch.load(tmp_path / "r1.pt", weights_only=False)
+    assert a["counts"].tolist() == b["counts"].tolist() == [5, 9]
+    assert sorted(a["means"]) == sorted(b["means"]) == [0, 1, 2, 3, 4, 5]
+    for w in a["means"]:
+        np.testing.assert_array_equal(a["means"][w], b["means"][w])
