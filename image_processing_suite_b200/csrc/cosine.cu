@@ -12,9 +12,26 @@
 // This file is the exact-fp32 CUDA-core path (float32 products, float64 accumulation of the
 // tile sums): it is what the parity tests pin to 1e-5.  The tensor-core path for the
 // single-huge-group case (config 5) lives in cosine_tc.cu.
+#include <stdlib.h>
+
 #include "ips_common.cuh"
 
 namespace ips {
+
+// cosine_tc.cu
+size_t cosine_tc_workspace_bytes(int N, int D);
+int cosine_tc_launch(const float* X, double* sum_out, int N, int D, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// One group of at least this many rows goes to the tensor cores (IPS_COSINE_TC=0 / 1 forces
+// the CUDA-core / tensor-core path for testing).
+constexpr int CS_TC_MIN_ROWS = 1024;
+static int cosine_tc_mode() {
+  static const int m = [] {
+    const char* s = getenv("IPS_COSINE_TC");
+    return (s && *s) ? atoi(s) : -1;
+  }();
+  return m;
+}
 
 constexpr int CS_TILE = 64;     // rows / cols of the Gram tile per block
 constexpr int CS_K = 16;        // depth of one shared-memory stage
@@ -144,7 +161,9 @@ using namespace ips;
 
 extern "C" size_t ips_cosine_workspace_bytes(int N, int D) {
   if (N <= 0 || D <= 0) return 0;
-  return round_up((size_t)N * D * sizeof(float), 256) + round_up((size_t)N * sizeof(unsigned long long), 256);
+  const size_t exact = round_up((size_t)N * D * sizeof(float), 256) + round_up((size_t)N * sizeof(unsigned long long), 256);
+  const size_t tc = cosine_tc_workspace_bytes(N, D) + 1024 + round_up((size_t)N * sizeof(unsigned long long), 256);
+  return exact > tc ? exact : tc;
 }
 
 extern "C" int ips_cosine_triu(const float* X, const int32_t* group, int n_groups, double* sum_out,
@@ -163,6 +182,23 @@ extern "C" int ips_cosine_triu(const float* X, const int32_t* group, int n_group
   const size_t need = ips_cosine_workspace_bytes(N, D);
   if (ws == nullptr || ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "ips_cosine_triu: needs %zu workspace bytes (got %zu)", need, ws_bytes);
   if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_cosine_triu: workspace not 16-byte aligned");
+  const int mode = cosine_tc_mode();
+  const bool use_tc = group == nullptr && N >= 2 && (mode == 1 || (mode != 0 && N >= CS_TC_MIN_ROWS));
+  if (use_tc) {
+    // counts live at the start of the workspace, the 1024-aligned bf16 planes behind them
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(ws);
+    cosine_zero_kernel<<<1, 32, 0, st>>>(sum_out, cnt, 1);
+    IPS_LAUNCH_OK("cosine_zero_kernel");
+    cosine_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(nullptr, cnt, N, 1);
+    IPS_LAUNCH_OK("cosine_count_kernel");
+    cosine_pairs_kernel<<<1, 32, 0, st>>>(cnt, np, 1);
+    IPS_LAUNCH_OK("cosine_pairs_kernel");
+    const size_t head = round_up((size_t)N * sizeof(unsigned long long), 256);
+    char* planes = reinterpret_cast<char*>(ws) + head;
+    planes = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(planes) + 1023) & ~(uintptr_t)1023);
+    const size_t left = ws_bytes - (size_t)(planes - reinterpret_cast<char*>(ws));
+    return cosine_tc_launch(X, sum_out, N, D, planes, left, st);
+  }
   float* Xn = reinterpret_cast<float*>(ws);
   unsigned long long* counts =
       reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + round_up((size_t)N * D * sizeof(float), 256));

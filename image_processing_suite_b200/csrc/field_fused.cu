@@ -188,7 +188,7 @@ static void launch_fused(int Z, int grid, cudaStream_t st, const uint16_t* raw, 
   // Occupancy is what hides the latency here (measured on B200, profiles/README.md): 4 CTAs
   // per SM (64 registers, no spills) beats 2 and 3 CTAs and a software-pipelined 1-CTA variant.
   // BIN = 4 holds a 4 x 8 window per lane and needs the larger register budget.
-  constexpr int MINB = BIN == 4 ? 2 : 4;
+  constexpr int MINB = BIN == 4 ? 4 : 8;
 #define IPS_FF_CASE(ZT)                                                           \
   field_fused_kernel<BIN, ZT, HAS_ILLUM, MINB><<<grid, OA_THREADS, 0, st>>>(      \
       raw, illum, labels, maxproj, binned, rec, flags, Nmax, F, C, Z, H, W, tiles_x)

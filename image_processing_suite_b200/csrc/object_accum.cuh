@@ -26,9 +26,9 @@
 
 namespace ips {
 
-constexpr int OA_WARPS = 8;
+constexpr int OA_WARPS = 4;
 constexpr int OA_THREADS = OA_WARPS * 32;
-constexpr int OA_CAP = 160;      // records per CTA; overflowing run heads flush directly
+constexpr int OA_CAP = 96;       // records per CTA; overflowing run heads flush directly
 constexpr int OA_PX = 8;
 constexpr int OA_CMAX = 8;
 constexpr unsigned OA_FULL = 0xffffffffu;

@@ -78,7 +78,7 @@ __device__ __forceinline__ void k3_load_chan(K3ChanRegs& R, const uint16_t* __re
 }
 
 template <bool HAS_ILLUM, bool VEC>
-__global__ void __launch_bounds__(OA_THREADS, 4)
+__global__ void __launch_bounds__(OA_THREADS, 8)
 object_stats_scan_kernel(const int32_t* __restrict__ labels, const uint16_t* __restrict__ maxproj,
                          const float* __restrict__ illum, unsigned long long* __restrict__ rec,
                          int* __restrict__ flags, int Nmax, int F, int C, int H, int W, int tiles_x) {

@@ -56,3 +56,20 @@ def test_cosine_single_group_closed_form_large():
     assert int(host(n)[0]) == 3000 * 2999 // 2
     ref = o_cos.triu_sum_closed_form(x.astype(np.float64))
     assert abs(float(host(s)[0]) - ref) / int(host(n)[0]) < ATOL
+
+
+@pytest.mark.parametrize("n,d", [(1024, 64), (1500, 200), (4100, 700), (2048, 3000)])
+def test_cosine_tensor_core_path_matches_closed_form(n, d):
+    """One group of >= 1024 rows runs on tcgen05 (bf16 hi/lo split, fp32 TMEM accumulators):
+    mean cosine within ATOL of the float64 oracle; exact pair count."""
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(n + d)
+    x = (rng.normal(size=(n, d)) + 0.2 * rng.normal(size=(1, d))).astype(np.float32)
+    x[7] = 0.0
+    s, npairs = ops.cosine_triu(dev(x))
+    assert int(host(npairs)[0]) == n * (n - 1) // 2
+    ref = o_cos.triu_sum_closed_form(x.astype(np.float64))
+    assert abs(float(host(s)[0]) - ref) / (n * (n - 1) // 2) < ATOL
+    if n <= 1500:
+        assert abs(float(host(s)[0]) - float(o_cos.triu_values(x.astype(np.float64)).sum())) / (n * (n - 1) // 2) < ATOL
