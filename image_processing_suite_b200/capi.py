@@ -54,6 +54,8 @@ PROTOTYPES = {
     "ips_cosine_triu": (i, [p, p, i, p, p, i, i, p, sz, p]),
     "ips_well_mean_workspace_bytes": (sz, [i, i]),
     "ips_well_mean": (i, [p, p, p, p, i, i, i, p, sz, p]),
+    "ips_mad_robustize": (i, [p, p, p, i, i, p]),
+    "ips_double_sigmoid_abs": (i, [p, p, i64, i, C.c_double, p]),
     "ips_pack_rows_workspace_bytes": (sz, [i]),
     "ips_pack_rows": (i, [p, p, p, p, i, p, p, i, i, i, p, sz, p]),
     "ips_rows_well_ids": (i, [p, p, p, i64, i, i, p]),

@@ -8,7 +8,7 @@
 // (Illumination_QC_mult.py:145-150, Cellpose_GPU_s3fs.py:72), north_star's sum re-binning and
 // the CellProfiler MeasureObject* subprocess (Feature_extraction_opt.py:166-167).
 //
-// Decomposition (object_accum.cuh): a CTA of 8 warps owns a 256-column x 8*BIN-row tile; a
+// Decomposition (object_accum.cuh): a CTA of 4 warps owns a 256-column x 4*BIN-row tile; a
 // lane owns BIN rows x 8 columns, i.e. one 128-bit word per row of every plane, and walks
 // the channels: Z x BIN 128-bit loads of raw data and 2 x BIN of the illumination function,
 // packed-uint16 max, store of the max projection, divide, bin, store of the binned row, then
@@ -185,9 +185,10 @@ template <int BIN, bool HAS_ILLUM>
 static void launch_fused(int Z, int grid, cudaStream_t st, const uint16_t* raw, const float* illum,
                          const int32_t* labels, uint16_t* maxproj, void* binned, unsigned long long* rec,
                          int* flags, int Nmax, int F, int C, int H, int W, int tiles_x) {
-  // Occupancy is what hides the latency here (measured on B200, profiles/README.md): 4 CTAs
-  // per SM (64 registers, no spills) beats 2 and 3 CTAs and a software-pipelined 1-CTA variant.
-  // BIN = 4 holds a 4 x 8 window per lane and needs the larger register budget.
+  // Occupancy is what hides the latency here (measured on B200, profiles/README.md): 64
+  // registers per thread (32 warps per SM, no spills) beats 80 and 118 registers and a
+  // software-pipelined 240-register variant.  BIN = 4 holds a 4 x 8 window per lane and needs
+  // the larger register budget.
   constexpr int MINB = BIN == 4 ? 4 : 8;
 #define IPS_FF_CASE(ZT)                                                           \
   field_fused_kernel<BIN, ZT, HAS_ILLUM, MINB><<<grid, OA_THREADS, 0, st>>>(      \

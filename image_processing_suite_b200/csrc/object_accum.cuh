@@ -1,16 +1,16 @@
 // Label-keyed segmented reduction machinery shared by K3 (object_stats.cu) and the fused
 // field kernel (field_fused.cu).
 //
-// Decomposition.  A CTA of 8 warps owns a tile of 256 columns x (8 * ROWS) rows: warp w owns
-// ROWS consecutive rows, lane l owns 8 consecutive columns of them (one 128-bit word per row
-// and plane).  Cellpose objects are compact, so
+// Decomposition.  A CTA of OA_WARPS (4) warps owns a tile of 256 columns x (4 * ROWS) rows: warp w
+// owns ROWS consecutive rows, lane l owns 8 consecutive columns of them (one 128-bit word per
+// row and plane).  Cellpose objects are compact, so
 //   * within a lane's ROWS x 8 window there are almost always at most two labels: the window
 //     is split into slot 1 (first label met), slot 2 (second label) and a rare remainder that
 //     is flushed pixel by pixel;
 //   * lanes next to each other mostly carry the same slot-1 label: runs of equal labels along
-//     the warp are reduced with a segmented shuffle tree (5 steps), so one lane per run -- the
-//     run head -- holds the run's partial;
-//   * the 8 warps of the CTA see the same objects in consecutive rows: run heads append their
+//     the warp are reduced with a segmented shuffle tree (runs are cut every 8 lanes: 3 steps),
+//     so one lane per run -- the run head -- holds the run's partial;
+//   * the warps of the CTA see the same objects in consecutive rows: run heads append their
 //     partials to a record list in shared memory, after a barrier records of equal label are
 //     merged, and each distinct label of the tile is flushed to its global accumulator record
 //     once (integer atomics for area / bbox / coordinate sums: exact and order independent;
@@ -26,7 +26,7 @@
 
 namespace ips {
 
-constexpr int OA_WARPS = 4;
+constexpr int OA_WARPS = 4;      // measured: 4-warp CTAs at 8 CTAs/SM beat 8-warp CTAs at 4 (shorter barrier waits)
 constexpr int OA_THREADS = OA_WARPS * 32;
 constexpr int OA_CAP = 96;       // records per CTA; overflowing run heads flush directly
 constexpr int OA_PX = 8;

@@ -11,7 +11,7 @@
 //                   every lane reads a 2 x 8 pixel window with 128-bit loads; the label-keyed
 //                   reduction runs lane -> warp (segmented shuffle tree) -> CTA (record list
 //                   in shared memory) -> global accumulators (atomics, once per object and
-//                   256 x 16 tile); see object_accum.cuh.
+//                   256 x 8 tile); see object_accum.cuh.
 //   3. compact   -- prefix-sum over "area > 0" and emit dense rows in ascending label order,
 //                   converting sums to mean / std / centroid (256 labels per block).
 // Blocks are numbered field-fastest so that the blocks reading the same piece of the
@@ -149,7 +149,7 @@ object_stats_scan_kernel(const int32_t* __restrict__ labels, const uint16_t* __r
     }
     oa_channel<K3_ROWS, HAS_ILLUM>(L, c, fv, iv, sh, rec_f, C);
   };
-  // Occupancy (4 CTAs per SM at 64 registers) hides the load latency better than a second
+  // Occupancy (8 four-warp CTAs per SM at 64 registers) hides the load latency better than a second
   // register set would (measured, profiles/README.md).  All-background rows are not loaded.
   if (__any_sync(OA_FULL, fg != 0u)) {
     for (int c = 0; c < C; ++c) {

@@ -364,3 +364,30 @@ def cosine_triu(X, group=None, n_groups=None):
         capi.call("ips_cosine_triu", _ptr(X), _ptr(group), int(n_groups), _ptr(s), _ptr(npairs), N, D,
                   _ptr(ws), ws.numel(), _stream(dev))
     return s, npairs
+
+
+# ---- profile normalisation -----------------------------------------------------------------
+def mad_robustize(profiles, is_control):
+    """(x - median_ctrl) / (1.4826 * MAD_ctrl + 1e-18) per feature column (device, float64).
+    profiles [W][D] float64, is_control [W] bool/uint8.  Replaces pycytominer's
+    normalize(method="mad_robustize") at Normalize_CP_ami.py:137-142."""
+    _check(profiles, "profiles", torch.float64, 2)
+    dev = profiles.device
+    ctrl = is_control.to(device=dev, dtype=torch.uint8).contiguous()
+    W, D = profiles.shape
+    if ctrl.shape[0] != W:
+        raise ValueError("one control flag per well expected")
+    with torch.cuda.device(dev):
+        out = torch.empty_like(profiles)
+        capi.call("ips_mad_robustize", _ptr(profiles), _ptr(ctrl), _ptr(out), W, D, _stream(dev))
+    return out
+
+
+def double_sigmoid_abs(x, k=3, alpha=2.3538):
+    """|double_sigmoid(x)| elementwise (Feature_select_cosine_ami.py:22-27, :117-118)."""
+    _check(x, "x", torch.float64)
+    dev = x.device
+    with torch.cuda.device(dev):
+        y = torch.empty_like(x)
+        capi.call("ips_double_sigmoid_abs", _ptr(x), _ptr(y), x.numel(), int(k), float(alpha), _stream(dev))
+    return y

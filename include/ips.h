@@ -174,6 +174,19 @@ size_t ips_well_mean_workspace_bytes(int n_wells, int D);
 int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
                   int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream);
 
+/* ---- robust-z normalisation of well profiles and the double sigmoid -------------------------
+ * Replaces  pycytominer normalize(method="mad_robustize", samples=<DMSO wells>)
+ *           Normalize_CP_ami.py:137-142, Pycyto_pertime.py:84-89:
+ *           out = (x - median_ctrl) / (1.4826 * MAD_ctrl + 1e-18) per feature column, the
+ *           statistics over the rows flagged in is_control (NaN ignored);
+ *      and  double_sigmoid(x, k, alpha).abs()   Feature_select_cosine_ami.py:22-27, :117-118.
+ * profiles / out [W][D] float64 (W <= 2048 wells), is_control [W] uint8.
+ */
+int ips_mad_robustize(const double* profiles, const uint8_t* is_control, double* out, int W, int D,
+                      ips_stream_t stream);
+int ips_double_sigmoid_abs(const double* x, double* y, int64_t n, int k, double alpha,
+                           ips_stream_t stream);
+
 /* ---- dense object rows (what the all-gather moves and the well aggregation reads) ---------
  * Compacts the padded per-field outputs of ips_object_stats / ips_field_fused into one
  * float32 row per object, the table the reference's consumers read from Nuclei.csv /

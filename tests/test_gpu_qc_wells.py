@@ -46,3 +46,30 @@ def test_well_mean_matches_pandas_groupby():
     perm = rng.permutation(5000)
     mean2, _ = ops.well_mean(dev(rows[perm]), dev(wells[perm]), n_wells)
     np.testing.assert_allclose(host(mean2)[ids], ref, rtol=1e-12)
+
+
+def test_mad_robustize_and_double_sigmoid_match_oracle():
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(8)
+    W, D = 384, 57
+    prof = rng.normal(50.0, 9.0, (W, D))
+    prof[5] = np.nan                                         # an empty well (no rows -> NaN means)
+    ctrl = np.zeros(W, bool)
+    ctrl[rng.choice(W, 33, replace=False)] = True
+    ctrl[5] = True                                           # NaN control is ignored (nanmedian)
+    prof[:, 3] = 7.0                                         # constant column: MAD 0 -> division by eps
+    z = host(ops.mad_robustize(dev(prof), dev(ctrl.astype(np.uint8))))
+    ref = o_norm.mad_robustize(prof, ctrl)
+    ok = np.isfinite(ref)
+    np.testing.assert_allclose(z[ok], ref[ok], rtol=1e-12, atol=1e-12)
+    assert np.isnan(np.delete(z[5], 3)).all() and z[5, 3] == 0.0
+    np.testing.assert_array_equal(z[:5, 3], 0.0)
+    zz = np.clip(z[np.isfinite(z)], -50, 50)
+    got = host(ops.double_sigmoid_abs(dev(zz)))
+    np.testing.assert_allclose(got, np.abs(o_norm.double_sigmoid(zz)), rtol=1e-12, atol=1e-15)
+    # even number of controls -> mean of the two middle values
+    ctrl2 = np.zeros(W, bool)
+    ctrl2[:4] = True
+    np.testing.assert_allclose(host(ops.mad_robustize(dev(prof[:, :2].copy()), dev(ctrl2.astype(np.uint8)))),
+                               o_norm.mad_robustize(prof[:, :2], ctrl2), rtol=1e-12)
