@@ -104,19 +104,28 @@ class RowGatherer:
             capi.call("ips_comm_create", C.byref(h), C.cast(uid, C.c_void_p), n, self.rank, self.world)
             self._comm = h
 
-    def gather(self, local_rows, n_local):
-        """local_rows [>= n_local][D] float32 -> (all_rows [world][cap][D], counts [world] int64)."""
+    def gather(self, local_rows, n_local, out=None):
+        """local_rows [>= n_local][D] float32 -> (all_rows [world][cap][D], counts [world] int64).
+
+        ``out`` = (all_rows, counts) reuses caller buffers; when ``local_rows`` already is
+        ``all_rows[rank]`` (rows packed in place) the staging copy is skipped."""
         n_local = int(n_local)
         if n_local > self.cap:
             raise ValueError("%d rows exceed the per-rank capacity %d" % (n_local, self.cap))
         if local_rows.dtype != torch.float32 or local_rows.dim() != 2 or local_rows.shape[1] != self.D:
             raise ValueError("rows must be float32 [n][%d]" % self.D)
         dev = local_rows.device
-        all_rows = torch.empty((self.world, self.cap, self.D), dtype=torch.float32, device=dev)
-        counts = torch.zeros((self.world,), dtype=torch.int64, device=dev)
+        if out is not None:
+            all_rows, counts = out
+            if tuple(all_rows.shape) != (self.world, self.cap, self.D) or not all_rows.is_contiguous():
+                raise ValueError("out rows must be contiguous [world][cap][D]")
+        else:
+            all_rows = torch.empty((self.world, self.cap, self.D), dtype=torch.float32, device=dev)
+            counts = torch.zeros((self.world,), dtype=torch.int64, device=dev)
         if self.world == 1:
-            all_rows[0, :n_local].copy_(local_rows[:n_local])
-            counts[0] = n_local
+            if local_rows.data_ptr() != all_rows.data_ptr():
+                all_rows[0, :n_local].copy_(local_rows[:n_local])
+            counts.fill_(n_local)
             return all_rows, counts
         if self.backend == "ips":
             with torch.cuda.device(dev):
