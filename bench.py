@@ -308,7 +308,7 @@ def gpu_arm(args):
     all_rows = torch.empty((n_chunks * world, cap, D_row), dtype=torch.float32, device=dev)
     all_counts = torch.zeros((n_chunks * world,), dtype=torch.int64, device=dev)
     gatherer = plate_mod.RowGatherer(cap, D_row)
-    agg_stream = torch.cuda.Stream(device=dev)
+    agg_stream = torch.cuda.Stream(device=dev, priority=-1)   # its few CTAs must not queue behind a full fused grid
     rows_seen = [0]
 
     def gather_chunk(g):
@@ -522,7 +522,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: one K1+K3 pass per step (ips_field_fused); split: K1 then K3")
-    ap.add_argument("--gather-chunks", type=int, default=4, help="pieces the plate's row all-gather is issued in")
+    ap.add_argument("--gather-chunks", type=int, default=8, help="pieces the plate's row all-gather is issued in")
     ap.add_argument("--batch", type=int, default=16, help="fields per step")
     ap.add_argument("--ring", type=int, default=32, help="distinct device-resident fields")
     ap.add_argument("--e2e-batch", type=int, default=4)

@@ -15,9 +15,22 @@
 // illumination function are adjacent in launch order, so it is fetched from HBM once per
 // launch and served from L2 (evict_last policy) to the other F-1 fields, while raw data
 // and outputs stream through with evict_first.
+#include <stdlib.h>
+
 #include "ips_common.cuh"
 
 namespace ips {
+
+// preprocess_tma.cu: the TMA-staged variant of this pass (IPS_K1_TMA=1 selects it)
+int preprocess_tma_try(const uint16_t* raw, const float* illum, uint16_t* maxproj, void* binned, int bin, int F,
+                       int C, int Z, int H, int W, cudaStream_t st);
+static bool k1_use_tma() {
+  static const bool v = [] {
+    const char* s = getenv("IPS_K1_TMA");
+    return s && *s && atoi(s) != 0;
+  }();
+  return v;
+}
 
 #define PCT_NEG_INF (__longlong_as_double(0xfff0000000000000ll))
 
@@ -380,6 +393,10 @@ extern "C" int ips_preprocess_fused(const uint16_t* raw, const float* illum, uin
     if (ws == nullptr || ws_bytes < need)
       IPS_FAIL(IPS_ERR_NOMEM, "ips_preprocess_fused: pct_maximal needs %zu workspace bytes (got %zu)", need, ws_bytes);
     if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_preprocess_fused: workspace not 16-byte aligned");
+  }
+  if (vec && !pct && corrected == nullptr && k1_use_tma()) {
+    const int rc = preprocess_tma_try(raw, illum, maxproj, binned, bin, F, C, Z, H, W, st);
+    if (rc <= 0) return rc;          // launched (0) or failed (< 0); 1 = shape not supported, fall through
   }
   if (vec) {
     if (illum != nullptr) {

@@ -1,15 +1,16 @@
 // Well-level aggregation of per-object rows: df.groupby("Metadata_Well").agg("mean")
 // (Normalize_CP_ami.py:126, Pycyto_pertime.py:69-72) -- the consumer of the all-gather.
 //
-// rows [N][D] float32 with a well id per row -> per-well float64 means.  Each block walks a
-// contiguous chunk of rows, thread d owns feature column d; consecutive rows of one well
-// (the common layout: rows arrive grouped by field, fields by well) are folded in a register
-// and flushed with one float64 atomic per (well, column) run.
+// rows [N][D] float32 with a well id per row -> per-well float64 means.  A thread owns one
+// feature column of a 32-row run; consecutive rows of one well (the common layout: rows
+// arrive grouped by field, fields by well) are folded in a register and flushed with one
+// float64 atomic per (well, column) run.
 #include "ips_common.cuh"
 
 namespace ips {
 
-constexpr int WM_ROWS = 256;   // rows per block
+constexpr int WM_ROWS = 32;        // rows per thread run
+constexpr int WM_THREADS = 256;
 
 __global__ void well_zero_kernel(double* sums, int* counts, size_t n_sums, int n_wells) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -17,34 +18,38 @@ __global__ void well_zero_kernel(double* sums, int* counts, size_t n_sums, int n
   if (i < (size_t)n_wells) counts[i] = 0;
 }
 
-__global__ void well_accumulate_kernel(const float* __restrict__ rows, const int32_t* __restrict__ well,
-                                       double* __restrict__ sums, int* __restrict__ counts,
-                                       int N, int D, int n_wells) {
-  const int r0 = blockIdx.x * WM_ROWS;
-  const int r1 = min(N, r0 + WM_ROWS);
-  for (int d = threadIdx.x; d < D + 1; d += blockDim.x) {   // column D = the row counter
-    int cur = -1;
-    double acc = 0.0;
-    int cnt = 0;
-    for (int r = r0; r < r1; ++r) {
-      const int w = well[r];
-      if (w < 0 || w >= n_wells) continue;   // rows without a well (id out of range) are dropped
-      if (w != cur) {
-        if (cur >= 0) {
-          if (d < D) atomicAdd(&sums[(size_t)cur * D + d], acc);
-          else atomicAdd(&counts[cur], cnt);
-        }
-        cur = w;
-        acc = 0.0;
-        cnt = 0;
+// Thread (sub, d): column d (d == D counts rows) of the 32-row run `sub` of the block.  The
+// threads of one run read consecutive floats of a row (coalesced); runs of one well fold in
+// a register and flush with one atomic.
+__global__ void __launch_bounds__(WM_THREADS)
+well_accumulate_kernel(const float* __restrict__ rows, const int32_t* __restrict__ well,
+                       double* __restrict__ sums, int* __restrict__ counts, long long N, int D, int n_wells,
+                       int cols, int subs) {
+  const int sub = threadIdx.x / cols, d = threadIdx.x - sub * cols;
+  if (sub >= subs) return;
+  const long long r0 = ((long long)blockIdx.x * subs + sub) * WM_ROWS;
+  if (r0 >= N) return;
+  const long long r1 = r0 + WM_ROWS < N ? r0 + WM_ROWS : N;
+  int cur = -1, cnt = 0;
+  double acc = 0.0;
+  for (long long r = r0; r < r1; ++r) {
+    const int w = well[r];
+    if (w < 0 || w >= n_wells) continue;   // rows without a well (id out of range) are dropped
+    if (w != cur) {
+      if (cur >= 0) {
+        if (d < D) atomicAdd(&sums[(size_t)cur * D + d], acc);
+        else atomicAdd(&counts[cur], cnt);
       }
-      if (d < D) acc += (double)rows[(size_t)r * D + d];
-      else ++cnt;
+      cur = w;
+      acc = 0.0;
+      cnt = 0;
     }
-    if (cur >= 0) {
-      if (d < D) atomicAdd(&sums[(size_t)cur * D + d], acc);
-      else atomicAdd(&counts[cur], cnt);
-    }
+    if (d < D) acc += (double)rows[(size_t)r * D + d];
+    else ++cnt;
+  }
+  if (cur >= 0) {
+    if (d < D) atomicAdd(&sums[(size_t)cur * D + d], acc);
+    else atomicAdd(&counts[cur], cnt);
   }
 }
 
@@ -86,8 +91,11 @@ extern "C" int ips_well_mean(const float* rows, const int32_t* well, double* mea
   well_zero_kernel<<<(unsigned)((n_sums + 255) / 256), 256, 0, st>>>(sums, counts, n_sums, n_wells);
   IPS_LAUNCH_OK("well_zero_kernel");
   if (N > 0) {
-    const int threads = D + 1 <= 32 ? 32 : (D + 1 <= 64 ? 64 : (D + 1 <= 128 ? 128 : 256));
-    well_accumulate_kernel<<<(N + WM_ROWS - 1) / WM_ROWS, threads, 0, st>>>(rows, well, sums, counts, N, D, n_wells);
+    if (D + 1 > WM_THREADS) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_mean: at most %d feature columns (got %d)", WM_THREADS - 1, D);
+    const int cols = D + 1, subs = WM_THREADS / cols;
+    const long long rows_per_block = (long long)subs * WM_ROWS;
+    const long long blocks = (N + rows_per_block - 1) / rows_per_block;
+    well_accumulate_kernel<<<(unsigned)blocks, WM_THREADS, 0, st>>>(rows, well, sums, counts, N, D, n_wells, cols, subs);
     IPS_LAUNCH_OK("well_accumulate_kernel");
   }
   well_finalize_kernel<<<(unsigned)((n_sums + 255) / 256), 256, 0, st>>>(sums, counts, mean_out, count_out, n_wells, D);

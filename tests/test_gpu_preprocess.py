@@ -126,3 +126,17 @@ def test_preprocess_full_size_properties():
     assert bool((again == b4).all())
     r1 = ops.preprocess_fused(r2["maxproj"][:, :, None].contiguous(), None, bin=1, want_binned=False)
     assert bool((r1["maxproj"].view(torch.int16) == r2["maxproj"].view(torch.int16)).all())
+
+
+def test_preprocess_tma_variant_passes_the_same_suite():
+    """IPS_K1_TMA=1 routes K1 through the TMA-staged kernel (cp.async.bulk + mbarrier ring);
+    the flag is read once per process, so the parity cases above are re-run in a child."""
+    require_gpu()
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, IPS_K1_TMA="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_preprocess.py", "-m", "gpu", "-q", "-x",
+                        "-k", "not tma_variant"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
