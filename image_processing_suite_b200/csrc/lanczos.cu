@@ -120,6 +120,102 @@ lanczos_v_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
   out[((size_t)p * OH + yy) * W + x] = pil_store_u16(ss);
 }
 
+// ---- shared-memory staged passes ---------------------------------------------------------------
+// The two kernels above issue one scalar load and one int -> double conversion per tap.  Here a
+// block first converts the input span it needs to double in shared memory (every input pixel
+// is converted once), then each thread accumulates its outputs tap by tap from shared memory in
+// exactly the same order (same __dmul_rn / __dadd_rn sequence, so the results are identical).
+constexpr int LZ_TX = 128;   // outputs along the filtered axis (h pass) / columns (v pass) per block
+constexpr int LZ_RH = 4;     // rows per block in the horizontal pass
+constexpr int LZ_RV = 8;     // output rows per block in the vertical pass
+
+__global__ void __launch_bounds__(LZ_TX)
+lanczos_h_staged_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                        const int* __restrict__ bounds, const double* __restrict__ kk, int ksize, int H,
+                        int W, int OW, int span_max) {
+  extern __shared__ double lz_s[];               // [LZ_RH][span_max] pixels, then [LZ_TX][ksize] weights
+  double* kk_s = lz_s + (size_t)LZ_RH * span_max;
+  const int p = blockIdx.z;
+  const int y0 = blockIdx.y * LZ_RH;
+  const int xo0 = blockIdx.x * LZ_TX;
+  const int xo1 = min(OW, xo0 + LZ_TX);
+  const int lo = bounds[2 * xo0];
+  const int hi = bounds[2 * (xo1 - 1)] + bounds[2 * (xo1 - 1) + 1];
+  const int span = hi - lo;
+#pragma unroll
+  for (int r = 0; r < LZ_RH; ++r) {
+    const int y = y0 + r;
+    const uint16_t* src = in + ((size_t)p * H + (y < H ? y : H - 1)) * W + lo;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < span; i += LZ_TX) lz_s[r * span_max + i] = (double)src[i];
+  }
+  // the weights of the block's outputs are one contiguous piece of the table
+  const double* kblk = kk + (size_t)xo0 * ksize;
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < (xo1 - xo0) * ksize; idx += LZ_TX) kk_s[idx] = kblk[idx];
+  __syncthreads();
+  const int xx = xo0 + threadIdx.x;
+  if (xx >= xo1) return;
+  const int xmin = bounds[2 * xx] - lo, n = bounds[2 * xx + 1];
+  const double* k = kk_s + (size_t)threadIdx.x * ksize;
+  double ss[LZ_RH];
+#pragma unroll
+  for (int r = 0; r < LZ_RH; ++r) ss[r] = 0.0;
+#pragma unroll 4
+  for (int t = 0; t < n; ++t) {
+    const double kt = k[t];
+#pragma unroll
+    for (int r = 0; r < LZ_RH; ++r) ss[r] = __dadd_rn(ss[r], __dmul_rn(lz_s[r * span_max + xmin + t], kt));
+  }
+#pragma unroll
+  for (int r = 0; r < LZ_RH; ++r)
+    if (y0 + r < H) out[((size_t)p * H + y0 + r) * OW + xx] = pil_store_u16(ss[r]);
+}
+
+__global__ void __launch_bounds__(LZ_TX)
+lanczos_v_staged_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                        const int* __restrict__ bounds, const double* __restrict__ kk, int ksize, int H,
+                        int W, int OH, int span_max) {
+  extern __shared__ double lz_s[];               // [span_max][LZ_TX] pixels, then [LZ_RV][ksize] weights
+  double* kk_s = lz_s + (size_t)span_max * LZ_TX;
+  const int p = blockIdx.z;
+  const int yy0 = blockIdx.y * LZ_RV;
+  const int yy1 = min(OH, yy0 + LZ_RV);
+  const int x = blockIdx.x * LZ_TX + threadIdx.x;
+  const int lo = bounds[2 * yy0];
+  const int hi = bounds[2 * (yy1 - 1)] + bounds[2 * (yy1 - 1) + 1];
+  const int span = hi - lo;
+  if (x < W) {
+    const uint16_t* col = in + ((size_t)p * H + lo) * W + x;
+#pragma unroll 8
+    for (int i = 0; i < span; ++i) lz_s[i * LZ_TX + threadIdx.x] = (double)col[(size_t)i * W];
+  }
+  for (int idx = threadIdx.x; idx < (yy1 - yy0) * ksize; idx += LZ_TX) kk_s[idx] = kk[(size_t)yy0 * ksize + idx];
+  __syncthreads();
+  if (x >= W) return;
+  for (int yy = yy0; yy < yy1; ++yy) {
+    const int ymin = bounds[2 * yy] - lo, n = bounds[2 * yy + 1];
+    const double* k = kk_s + (size_t)(yy - yy0) * ksize;
+    double ss = 0.0;
+#pragma unroll 4
+    for (int t = 0; t < n; ++t) ss = __dadd_rn(ss, __dmul_rn(lz_s[(ymin + t) * LZ_TX + threadIdx.x], k[t]));
+    out[((size_t)p * OH + yy) * W + x] = pil_store_u16(ss);
+  }
+}
+
+// largest input span any block of `per_block` consecutive outputs needs
+static int lanczos_span_max(const LanczosCoeffs& c, int n_out, int per_block) {
+  int m = 1;
+  for (int o0 = 0; o0 < n_out; o0 += per_block) {
+    const int o1 = (o0 + per_block < n_out ? o0 + per_block : n_out) - 1;
+    const int span = c.bounds[(size_t)o1 * 2] + c.bounds[(size_t)o1 * 2 + 1] - c.bounds[(size_t)o0 * 2];
+    if (span > m) m = span;
+  }
+  return m;
+}
+
+constexpr size_t LZ_SMEM_LIMIT = 96 * 1024;   // keeps at least two blocks per SM
+
 struct LanczosLayout {
   size_t tmp, hb, hk, vb, vk, total;
 };
@@ -176,8 +272,17 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
     IPS_CUDA_OK(cudaMemcpyAsync(db, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     IPS_CUDA_OK(cudaMemcpyAsync(dk, c.kk.data(), c.kk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     uint16_t* h_out = need_v ? tmp : out;
-    lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW);
-    IPS_LAUNCH_OK("lanczos_h_kernel");
+    const int span_max = lanczos_span_max(c, outW, LZ_TX);
+    const size_t smem = ((size_t)LZ_RH * span_max + (size_t)LZ_TX * c.ksize) * sizeof(double);
+    if (smem <= LZ_SMEM_LIMIT && (H + LZ_RH - 1) / LZ_RH <= 65535) {
+      IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_h_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lanczos_h_staged_kernel<<<dim3((outW + LZ_TX - 1) / LZ_TX, (H + LZ_RH - 1) / LZ_RH, C), LZ_TX, smem, st>>>(
+          in, h_out, db, dk, c.ksize, H, W, outW, span_max);
+      IPS_LAUNCH_OK("lanczos_h_staged_kernel");
+    } else {
+      lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW);
+      IPS_LAUNCH_OK("lanczos_h_kernel");
+    }
     v_in = h_out;
     v_W = outW;
   }
@@ -187,8 +292,17 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
     double* dk = reinterpret_cast<double*>(base + L.vk);
     IPS_CUDA_OK(cudaMemcpyAsync(db, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     IPS_CUDA_OK(cudaMemcpyAsync(dk, c.kk.data(), c.kk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH);
-    IPS_LAUNCH_OK("lanczos_v_kernel");
+    const int span_max = lanczos_span_max(c, outH, LZ_RV);
+    const size_t smem = ((size_t)span_max * LZ_TX + (size_t)LZ_RV * c.ksize) * sizeof(double);
+    if (smem <= LZ_SMEM_LIMIT) {
+      IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_v_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lanczos_v_staged_kernel<<<dim3((v_W + LZ_TX - 1) / LZ_TX, (outH + LZ_RV - 1) / LZ_RV, C), LZ_TX, smem, st>>>(
+          v_in, out, db, dk, c.ksize, H, v_W, outH, span_max);
+      IPS_LAUNCH_OK("lanczos_v_staged_kernel");
+    } else {
+      lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH);
+      IPS_LAUNCH_OK("lanczos_v_kernel");
+    }
   }
   return IPS_OK;
 }
