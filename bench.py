@@ -404,15 +404,16 @@ def gpu_arm(args):
     e2e = None
     Fe = args.e2e_batch
     n_host = args.e2e_ring
+    # label masks travel as uint16, the dtype Cellpose writes them in (Cellpose_GPU_s3fs.py:143)
     pipe = FieldPipeline(Fe, C_, Z_, H_, W_, bin=BIN, n_max=n_max, depth=3, illum=illum_host,
-                         intensity_scale=scale)
+                         intensity_scale=scale, label_dtype=np.uint16)
     h_raw = [pinned_empty((Fe, C_, Z_, H_, W_), np.uint16) for _ in range(n_host)]
-    h_lab = [pinned_empty((Fe, H_, W_), np.int32) for _ in range(n_host)]
+    h_lab = [pinned_empty((Fe, H_, W_), np.uint16) for _ in range(n_host)]
     for j in range(n_host):
         for k in range(Fe):
             src = (j * Fe + k) % R
             h_raw[j][k] = raw[src].cpu().numpy()
-            h_lab[j][k] = labels[src].cpu().numpy()
+            h_lab[j][k] = labels[src].cpu().numpy().astype(np.uint16)
     h_out = [pipe.output_buffers() for _ in range(3)]
     e2e_steps = max(1, args.e2e_fields // Fe)
     for i in range(3):

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "ips_allgather_rows": (i, [p, p, i64, i, p, p, i64, p]),
     "ips_host_alloc": (i, [C.POINTER(p), sz]),
     "ips_host_free": (i, [p]),
-    "ips_pipeline_create": (i, [C.POINTER(p), i, i, i, i, i, i, i, i, p, f]),
+    "ips_pipeline_create": (i, [C.POINTER(p), i, i, i, i, i, i, i, i, i, p, f]),
     "ips_pipeline_submit": (i64, [p, p, p, p, p, p, p, p]),
     "ips_pipeline_wait": (i, [p, i64]),
     "ips_pipeline_destroy": (i, [p]),

@@ -14,9 +14,26 @@
 
 namespace ips {
 
+// uint16 label masks (what Cellpose writes when a field has < 65536 objects) are widened on the
+// device: 9.3 MB less over PCIe per 2160^2 field for 28 MB of extra HBM traffic.
+__global__ void __launch_bounds__(256)
+widen_labels_kernel(const uint16_t* __restrict__ in, int32_t* __restrict__ out, size_t n_words /* n / 8 */,
+                    size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) {
+    const uint4 v = reinterpret_cast<const uint4*>(in)[i];
+    uint4* o = reinterpret_cast<uint4*>(out) + 2 * i;
+    o[0] = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+    o[1] = make_uint4(v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16);
+  }
+  if (i == 0)
+    for (size_t k = n_words * 8; k < n; ++k) out[k] = in[k];
+}
+
 struct Slot {
   uint16_t* raw = nullptr;
   int32_t* labels = nullptr;
+  uint16_t* labels16 = nullptr;
   uint16_t* maxproj = nullptr;
   void* binned = nullptr;
   int32_t* n_objects = nullptr;
@@ -30,7 +47,7 @@ struct Slot {
 }  // namespace ips
 
 struct ips_pipeline {
-  int Fb, C, Z, H, W, bin, Nmax, depth;
+  int Fb, C, Z, H, W, bin, Nmax, depth, label_bytes;
   float scale;
   float* illum = nullptr;
   size_t ws_bytes = 0;
@@ -45,7 +62,7 @@ using namespace ips;
 static void pipeline_free(ips_pipeline* p) {
   if (p == nullptr) return;
   for (Slot& s : p->slots) {
-    cudaFree(s.raw); cudaFree(s.labels); cudaFree(s.maxproj); cudaFree(s.binned);
+    cudaFree(s.raw); cudaFree(s.labels); cudaFree(s.labels16); cudaFree(s.maxproj); cudaFree(s.binned);
     cudaFree(s.n_objects); cudaFree(s.ints); cudaFree(s.flts); cudaFree(s.ws);
     if (s.h2d_done) cudaEventDestroy(s.h2d_done);
     if (s.compute_done) cudaEventDestroy(s.compute_done);
@@ -70,8 +87,8 @@ static void pipeline_free(ips_pipeline* p) {
   } while (0)
 
 extern "C" int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, int C, int Z, int H,
-                                   int W, int bin, int Nmax, int depth, const float* illum_host,
-                                   float intensity_scale) {
+                                   int W, int bin, int Nmax, int depth, int label_bytes,
+                                   const float* illum_host, float intensity_scale) {
   if (out == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_pipeline_create: out is NULL");
   *out = nullptr;
   if (fields_per_batch <= 0 || C <= 0 || C > 8 || Z <= 0 || H <= 0 || W <= 0 || Nmax <= 0)
@@ -80,10 +97,12 @@ extern "C" int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, i
   if (bin != 1 && bin != 2 && bin != 4) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_pipeline_create: bin must be 1, 2 or 4");
   if (H % bin || W % bin) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_pipeline_create: %dx%d not divisible by bin %d", H, W, bin);
   if (depth < 1 || depth > 16) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_pipeline_create: depth must be in 1..16");
+  if (label_bytes != 2 && label_bytes != 4)
+    IPS_FAIL(IPS_ERR_BAD_DTYPE, "ips_pipeline_create: labels must be uint16 (2) or int32 (4), got %d bytes", label_bytes);
   ips_pipeline* p = new (std::nothrow) ips_pipeline();
   if (p == nullptr) IPS_FAIL(IPS_ERR_NOMEM, "ips_pipeline_create: out of host memory");
   p->Fb = fields_per_batch; p->C = C; p->Z = Z; p->H = H; p->W = W; p->bin = bin; p->Nmax = Nmax;
-  p->depth = depth; p->scale = intensity_scale;
+  p->depth = depth; p->scale = intensity_scale; p->label_bytes = label_bytes;
   const size_t plane = (size_t)H * W, Fb = (size_t)fields_per_batch;
   PIPE_CUDA_OK(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
   PIPE_CUDA_OK(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
@@ -97,6 +116,7 @@ extern "C" int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, i
   for (Slot& s : p->slots) {
     PIPE_CUDA_OK(cudaMalloc(&s.raw, Fb * C * Z * plane * sizeof(uint16_t)));
     PIPE_CUDA_OK(cudaMalloc(&s.labels, Fb * plane * sizeof(int32_t)));
+    if (label_bytes == 2) PIPE_CUDA_OK(cudaMalloc(&s.labels16, Fb * plane * sizeof(uint16_t)));
     PIPE_CUDA_OK(cudaMalloc(&s.maxproj, Fb * C * plane * sizeof(uint16_t)));
     PIPE_CUDA_OK(cudaMalloc(&s.binned, Fb * C * (plane / (bin * bin)) * 4));
     PIPE_CUDA_OK(cudaMalloc(&s.n_objects, Fb * sizeof(int32_t)));
@@ -112,7 +132,7 @@ extern "C" int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, i
 }
 
 extern "C" int64_t ips_pipeline_submit(ips_pipeline_t* p, const uint16_t* raw_host,
-                                       const int32_t* labels_host, uint16_t* maxproj_host,
+                                       const void* labels_host, uint16_t* maxproj_host,
                                        void* binned_host, int32_t* n_objects_host,
                                        int32_t* ints_host, float* flts_host) {
   if (p == nullptr || raw_host == nullptr || labels_host == nullptr)
@@ -125,10 +145,17 @@ extern "C" int64_t ips_pipeline_submit(ips_pipeline_t* p, const uint16_t* raw_ho
   if (s.ticket >= 0) IPS_CUDA_OK(cudaStreamWaitEvent(p->s_in, s.d2h_done, 0));
   IPS_CUDA_OK(cudaMemcpyAsync(s.raw, raw_host, Fb * C * p->Z * plane * sizeof(uint16_t),
                               cudaMemcpyHostToDevice, p->s_in));
-  IPS_CUDA_OK(cudaMemcpyAsync(s.labels, labels_host, Fb * plane * sizeof(int32_t),
-                              cudaMemcpyHostToDevice, p->s_in));
+  if (p->label_bytes == 4)
+    IPS_CUDA_OK(cudaMemcpyAsync(s.labels, labels_host, Fb * plane * sizeof(int32_t), cudaMemcpyHostToDevice, p->s_in));
+  else
+    IPS_CUDA_OK(cudaMemcpyAsync(s.labels16, labels_host, Fb * plane * sizeof(uint16_t), cudaMemcpyHostToDevice, p->s_in));
   IPS_CUDA_OK(cudaEventRecord(s.h2d_done, p->s_in));
   IPS_CUDA_OK(cudaStreamWaitEvent(p->s_compute, s.h2d_done, 0));
+  if (p->label_bytes == 2) {
+    const size_t n = Fb * plane, words = n / 8;
+    widen_labels_kernel<<<(unsigned)((words + 256) / 256), 256, 0, p->s_compute>>>(s.labels16, s.labels, words, n);
+    IPS_LAUNCH_OK("widen_labels_kernel");
+  }
   const int rc = ips_field_fused(s.raw, p->illum, s.labels, s.maxproj, s.binned, p->bin, p->scale,
                                  s.n_objects, s.ints, s.flts, p->Nmax, s.ws, p->ws_bytes, p->Fb, p->C,
                                  p->Z, p->H, p->W, p->s_compute);

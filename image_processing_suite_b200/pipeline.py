@@ -45,17 +45,20 @@ class FieldPipeline:
     """depth-slot H2D -> K1 -> K3 -> D2H pipeline for batches of ``fields_per_batch`` fields."""
 
     def __init__(self, fields_per_batch, C_, Z, H, W, bin=2, n_max=2048, depth=3, illum=None,
-                 intensity_scale=1.0):
+                 intensity_scale=1.0, label_dtype=np.int32):
         self.shape = (int(fields_per_batch), int(C_), int(Z), int(H), int(W))
         self.bin, self.n_max = int(bin), int(n_max)
         self.has_illum = illum is not None
+        self.label_dtype = np.dtype(label_dtype)
+        if self.label_dtype not in (np.dtype(np.int32), np.dtype(np.uint16)):
+            raise TypeError("label masks must be int32 or uint16")
         if illum is not None:
             illum = np.ascontiguousarray(illum, dtype=np.float32)
             if illum.shape != (C_, H, W):
                 raise ValueError("illum shape %s != %s" % (illum.shape, (C_, H, W)))
         self._h = C.c_void_p()
         capi.call("ips_pipeline_create", C.byref(self._h), fields_per_batch, C_, Z, H, W, bin, n_max,
-                  depth, _hp(illum), float(intensity_scale))
+                  depth, self.label_dtype.itemsize, _hp(illum), float(intensity_scale))
 
     def output_buffers(self):
         """A dict of page-locked host output arrays for one batch."""
@@ -78,7 +81,7 @@ class FieldPipeline:
     def submit(self, raw, labels, out):
         Fb, Cn, Z, H, W = self.shape
         self._chk(raw, (Fb, Cn, Z, H, W), np.uint16, "raw")
-        self._chk(labels, (Fb, H, W), np.int32, "labels")
+        self._chk(labels, (Fb, H, W), self.label_dtype, "labels")
         bdt = np.float32 if self.has_illum else np.uint32
         self._chk(out.get("maxproj"), (Fb, Cn, H, W), np.uint16, "out.maxproj")
         self._chk(out.get("binned"), (Fb, Cn, H // self.bin, W // self.bin), bdt, "out.binned")
@@ -94,7 +97,7 @@ class FieldPipeline:
 
     def h2d_bytes(self):
         Fb, Cn, Z, H, W = self.shape
-        return Fb * (Cn * Z * H * W * 2 + H * W * 4)
+        return Fb * (Cn * Z * H * W * 2 + H * W * self.label_dtype.itemsize)
 
     def d2h_bytes(self, out):
         return int(sum(a.nbytes for a in out.values() if a is not None))

@@ -230,13 +230,15 @@ int ips_allgather_rows(void* comm, const void* local_rows, int64_t n_local, int 
 typedef struct ips_pipeline ips_pipeline_t;
 int ips_host_alloc(void** out, size_t bytes);
 int ips_host_free(void* p);
+/* label_bytes: 2 = uint16 label masks (Cellpose's own dtype below 65536 objects,
+ * Cellpose_GPU_s3fs.py:143; widened on the device), 4 = int32. */
 int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, int C, int Z, int H, int W,
-                        int bin, int Nmax, int depth, const float* illum_host /* or NULL */,
-                        float intensity_scale);
+                        int bin, int Nmax, int depth, int label_bytes,
+                        const float* illum_host /* or NULL */, float intensity_scale);
 /* Enqueue one batch; returns a ticket (>= 0) or a negative error.  Output pointers may be
  * NULL to skip that device->host copy. */
 int64_t ips_pipeline_submit(ips_pipeline_t* p, const uint16_t* raw_host,
-                            const int32_t* labels_host, uint16_t* maxproj_host,
+                            const void* labels_host, uint16_t* maxproj_host,
                             void* binned_host, int32_t* n_objects_host, int32_t* ints_host,
                             float* flts_host);
 int ips_pipeline_wait(ips_pipeline_t* p, int64_t ticket); /* blocks until that batch's outputs landed */

@@ -10,18 +10,19 @@ from tests.gpu_util import require_gpu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("with_illum", [True, False])
-def test_pipeline_batches_match_oracle(with_illum):
+@pytest.mark.parametrize("with_illum,label_dtype", [(True, np.int32), (False, np.int32), (True, np.uint16)])
+def test_pipeline_batches_match_oracle(with_illum, label_dtype):
     require_gpu()
     from image_processing_suite_b200.pipeline import FieldPipeline, pinned_empty
     Fb, C, Z, H, W, cells, n_batches = 2, 3, 3, 96, 128, 12, 5
     ill = synth.make_illum(C, H, W, seed=5) if with_illum else None
     scale = 1.0 / 65535.0 if with_illum else 1.0
-    pipe = FieldPipeline(Fb, C, Z, H, W, bin=2, n_max=cells, depth=2, illum=ill, intensity_scale=scale)
+    pipe = FieldPipeline(Fb, C, Z, H, W, bin=2, n_max=cells, depth=2, illum=ill, intensity_scale=scale,
+                         label_dtype=label_dtype)
     raws, labs, outs, tickets = [], [], [], []
     for b in range(n_batches):
         raw = pinned_empty((Fb, C, Z, H, W), np.uint16)
-        lab = pinned_empty((Fb, H, W), np.int32)
+        lab = pinned_empty((Fb, H, W), label_dtype)
         for k in range(Fb):
             lab[k] = synth.make_labels(H, W, cells, seed=10 * b + k, amin=5, amax=10)
             raw[k] = synth.field_numpy(lab[k], c=C, z=Z, seed=10 * b + k)
