@@ -55,12 +55,33 @@ field_fused_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ i
       for (int i = 0; i < OA_PX; ++i) lab[r][i] = 0;
     }
   }
+  // Pull channel c's rows towards L2 one channel ahead of their use: at 64 registers there is
+  // no room for a second register set, but a prefetch needs none.  One lane in four (u16
+  // rows: 64 bytes apart) / in two (float rows) touches every 128-byte line of the warp's span.
+  auto prefetch_channel = [&](int c) {
+    if (!active) return;
+    if ((lane & 3) == 0) {
+      const uint16_t* rp = raw + ((size_t)f * C + c) * nz * plane + (size_t)y0 * W + x0;
+      for (int z = 0; z < nz; ++z)
+#pragma unroll
+        for (int r = 0; r < BIN; ++r)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)z * plane + (size_t)r * W));
+    }
+    if (HAS_ILLUM && (lane & 1) == 0) {
+      const float* ip = illum + (size_t)c * plane + (size_t)y0 * W + x0;
+#pragma unroll
+      for (int r = 0; r < BIN; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(ip + (size_t)r * W));
+    }
+  };
+  prefetch_channel(0);
+
   bool overflow = false;
   OaLane<BIN> L;
   oa_begin<BIN>(L, lab, lp, W, Nmax, y0, x0, sh, rec_f, C, overflow);
   const bool warp_fg = __any_sync(OA_FULL, (L.m1 | L.m2 | L.m3) != 0u);
 
   for (int c = 0; c < C; ++c) {
+    if (c + 1 < C) prefetch_channel(c + 1);   // distance 1 measured best (0.744 ms vs 0.767 at distance 2, 0.781 without)
     const size_t fc = (size_t)f * C + c;
     uint4 m[BIN];
     uint4 il[BIN][2];
