@@ -308,6 +308,7 @@ def gpu_arm(args):
     all_rows = torch.empty((n_chunks * world, cap, D_row), dtype=torch.float32, device=dev)
     all_counts = torch.zeros((n_chunks * world,), dtype=torch.int64, device=dev)
     gatherer = plate_mod.RowGatherer(cap, D_row)
+    well_agg = plate_mod.WellAggregator(n_wells, D_row, device=dev)
     agg_stream = torch.cuda.Stream(device=dev, priority=-1)   # its few CTAs must not queue behind a full fused grid
     rows_seen = [0]
 
@@ -324,14 +325,20 @@ def gpu_arm(args):
                                            field_base=g * chunk_fields, out=mine)
             n = int(total.item())
             rows_seen[0] += n
-            gatherer.gather(mine, n, out=(all_rows[g * world:(g + 1) * world], all_counts[g * world:(g + 1) * world]))
+            blk = (all_rows[g * world:(g + 1) * world], all_counts[g * world:(g + 1) * world])
+            gatherer.gather(mine, n, out=blk)
+            well_agg.add(*blk)                              # per-well sums of this chunk, still on the side stream
 
     def finish_plate():
+        with torch.cuda.stream(agg_stream):
+            res = well_agg.finalize()
         torch.cuda.current_stream().wait_stream(agg_stream)
-        return plate_mod.well_means(all_rows, all_counts, n_wells)
+        return res
 
     def aggregate_all():
         rows_seen[0] = 0
+        with torch.cuda.stream(agg_stream):
+            well_agg.reset()
         for g in range(n_chunks):
             gather_chunk(g)
         return finish_plate()
@@ -376,6 +383,8 @@ def gpu_arm(args):
         t_begin.record()
         rows_seen[0] = 0
         chunks_done = 0
+        with torch.cuda.stream(agg_stream):
+            well_agg.reset()
         for i in range(args.steps):
             step(i, evs[i])
             if args.steps == n_slots and (i + 1) % slots_per_chunk == 0 and chunks_done < n_chunks:

@@ -76,29 +76,68 @@ extern "C" size_t ips_well_mean_workspace_bytes(int n_wells, int D) {
   return wm_sums_bytes(n_wells, D) + wm_counts_bytes(n_wells);
 }
 
-extern "C" int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
-                             int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream) {
-  if (!mean_out || !count_out || !ws) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_mean: NULL pointer argument");
-  if (N > 0 && (!rows || !well)) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_mean: NULL rows");
-  if (N < 0 || D <= 0 || n_wells <= 0) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_mean: bad shape N=%d D=%d n_wells=%d", N, D, n_wells);
+static int wm_check(const void* ws, size_t ws_bytes, int D, int n_wells, const char* who) {
+  if (ws == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "%s: NULL workspace", who);
+  if (D <= 0 || n_wells <= 0) IPS_FAIL(IPS_ERR_BAD_SHAPE, "%s: bad shape D=%d n_wells=%d", who, D, n_wells);
+  if (D + 1 > WM_THREADS) IPS_FAIL(IPS_ERR_BAD_SHAPE, "%s: at most %d feature columns (got %d)", who, WM_THREADS - 1, D);
   const size_t need = ips_well_mean_workspace_bytes(n_wells, D);
-  if (ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "ips_well_mean: needs %zu workspace bytes (got %zu)", need, ws_bytes);
-  if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_well_mean: workspace not 16-byte aligned");
+  if (ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "%s: needs %zu workspace bytes (got %zu)", who, need, ws_bytes);
+  if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "%s: workspace not 16-byte aligned", who);
+  return IPS_OK;
+}
+
+// The streaming form: reset once, add row blocks as they arrive (e.g. one all-gather chunk at a
+// time, overlapping the next chunk's transfer), finalize once.
+extern "C" int ips_well_sums_reset(void* ws, size_t ws_bytes, int D, int n_wells, ips_stream_t stream) {
+  const int rc = wm_check(ws, ws_bytes, D, n_wells, "ips_well_sums_reset");
+  if (rc != IPS_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   double* sums = reinterpret_cast<double*>(ws);
   int* counts = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + wm_sums_bytes(n_wells, D));
   const size_t n_sums = (size_t)n_wells * D;
   well_zero_kernel<<<(unsigned)((n_sums + 255) / 256), 256, 0, st>>>(sums, counts, n_sums, n_wells);
   IPS_LAUNCH_OK("well_zero_kernel");
-  if (N > 0) {
-    if (D + 1 > WM_THREADS) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_mean: at most %d feature columns (got %d)", WM_THREADS - 1, D);
-    const int cols = D + 1, subs = WM_THREADS / cols;
-    const long long rows_per_block = (long long)subs * WM_ROWS;
-    const long long blocks = (N + rows_per_block - 1) / rows_per_block;
-    well_accumulate_kernel<<<(unsigned)blocks, WM_THREADS, 0, st>>>(rows, well, sums, counts, N, D, n_wells, cols, subs);
-    IPS_LAUNCH_OK("well_accumulate_kernel");
-  }
+  return IPS_OK;
+}
+
+extern "C" int ips_well_sums_add(const float* rows, const int32_t* well, int64_t N, void* ws, size_t ws_bytes, int D,
+                                 int n_wells, ips_stream_t stream) {
+  const int rc = wm_check(ws, ws_bytes, D, n_wells, "ips_well_sums_add");
+  if (rc != IPS_OK) return rc;
+  if (N < 0) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_sums_add: negative row count");
+  if (N == 0) return IPS_OK;
+  if (!rows || !well) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_sums_add: NULL rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* sums = reinterpret_cast<double*>(ws);
+  int* counts = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + wm_sums_bytes(n_wells, D));
+  const int cols = D + 1, subs = WM_THREADS / cols;
+  const long long rows_per_block = (long long)subs * WM_ROWS;
+  const long long blocks = (N + rows_per_block - 1) / rows_per_block;
+  if (blocks > 0x7fffffffLL) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_sums_add: too many rows for one call");
+  well_accumulate_kernel<<<(unsigned)blocks, WM_THREADS, 0, st>>>(rows, well, sums, counts, N, D, n_wells, cols, subs);
+  IPS_LAUNCH_OK("well_accumulate_kernel");
+  return IPS_OK;
+}
+
+extern "C" int ips_well_sums_finalize(const void* ws, size_t ws_bytes, double* mean_out, int32_t* count_out, int D,
+                                      int n_wells, ips_stream_t stream) {
+  const int rc = wm_check(ws, ws_bytes, D, n_wells, "ips_well_sums_finalize");
+  if (rc != IPS_OK) return rc;
+  if (!mean_out || !count_out) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_sums_finalize: NULL output");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const double* sums = reinterpret_cast<const double*>(ws);
+  const int* counts = reinterpret_cast<const int*>(reinterpret_cast<const char*>(ws) + wm_sums_bytes(n_wells, D));
+  const size_t n_sums = (size_t)n_wells * D;
   well_finalize_kernel<<<(unsigned)((n_sums + 255) / 256), 256, 0, st>>>(sums, counts, mean_out, count_out, n_wells, D);
   IPS_LAUNCH_OK("well_finalize_kernel");
   return IPS_OK;
+}
+
+extern "C" int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
+                             int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream) {
+  if (N < 0) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_mean: negative row count");
+  int rc = ips_well_sums_reset(ws, ws_bytes, D, n_wells, stream);
+  if (rc == IPS_OK) rc = ips_well_sums_add(rows, well, N, ws, ws_bytes, D, n_wells, stream);
+  if (rc == IPS_OK) rc = ips_well_sums_finalize(ws, ws_bytes, mean_out, count_out, D, n_wells, stream);
+  return rc;
 }

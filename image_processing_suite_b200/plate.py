@@ -164,3 +164,36 @@ def well_means(all_rows, counts, n_wells):
     from . import ops
     world, cap, D = all_rows.shape
     return ops.well_mean(all_rows.reshape(world * cap, D), well_ids_of(all_rows, counts), n_wells)
+
+
+class WellAggregator:
+    """Streaming per-well means: ``add`` gathered row blocks as they arrive (one all-gather
+    chunk at a time), ``finalize`` once per plate.  Same arithmetic as ``well_means``."""
+
+    def __init__(self, n_wells, D, device="cuda"):
+        self.n_wells, self.D = int(n_wells), int(D)
+        self.dev = torch.device(device)
+        with torch.cuda.device(self.dev):
+            n = int(capi.call("ips_well_mean_workspace_bytes", self.n_wells, self.D))
+            self.ws = torch.empty(max(n, 16), dtype=torch.uint8, device=self.dev)
+        self.reset()
+
+    def reset(self):
+        with torch.cuda.device(self.dev):
+            capi.call("ips_well_sums_reset", _ptr(self.ws), self.ws.numel(), self.D, self.n_wells, _stream(self.dev))
+
+    def add(self, all_rows, counts):
+        """all_rows [blocks][cap][D] float32 with the first counts[b] rows of block b valid."""
+        ids = well_ids_of(all_rows, counts)
+        blocks, cap, D = all_rows.shape
+        with torch.cuda.device(self.dev):
+            capi.call("ips_well_sums_add", _ptr(all_rows), _ptr(ids), blocks * cap, _ptr(self.ws), self.ws.numel(),
+                      self.D, self.n_wells, _stream(self.dev))
+
+    def finalize(self):
+        with torch.cuda.device(self.dev):
+            mean = torch.empty((self.n_wells, self.D), dtype=torch.float64, device=self.dev)
+            count = torch.empty((self.n_wells,), dtype=torch.int32, device=self.dev)
+            capi.call("ips_well_sums_finalize", _ptr(self.ws), self.ws.numel(), _ptr(mean), _ptr(count), self.D,
+                      self.n_wells, _stream(self.dev))
+        return mean, count

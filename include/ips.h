@@ -173,6 +173,13 @@ int ips_cosine_triu(const float* X, const int32_t* group, int n_groups, double* 
 size_t ips_well_mean_workspace_bytes(int n_wells, int D);
 int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
                   int N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream);
+/* Streaming form of the same aggregation (same workspace): reset once, add row blocks as they
+ * arrive -- e.g. one all-gather chunk at a time -- finalize once. */
+int ips_well_sums_reset(void* ws, size_t ws_bytes, int D, int n_wells, ips_stream_t stream);
+int ips_well_sums_add(const float* rows, const int32_t* well, int64_t N, void* ws, size_t ws_bytes,
+                      int D, int n_wells, ips_stream_t stream);
+int ips_well_sums_finalize(const void* ws, size_t ws_bytes, double* mean_out, int32_t* count_out,
+                           int D, int n_wells, ips_stream_t stream);
 
 /* ---- robust-z normalisation of well profiles and the double sigmoid -------------------------
  * Replaces  pycytominer normalize(method="mad_robustize", samples=<DMSO wells>)

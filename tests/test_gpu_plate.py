@@ -40,3 +40,24 @@ def test_pack_rows_and_well_means_match_groupby():
     np.testing.assert_allclose(m[ids], ref, rtol=1e-12)
     assert c.sum() == n and set(np.flatnonzero(c)) == set(ids.tolist())
     assert np.isnan(m[0]).all()
+
+
+def test_well_aggregator_streaming_equals_one_shot():
+    torch = require_gpu()
+    from image_processing_suite_b200 import plate
+    rng = np.random.default_rng(3)
+    blocks, cap, D, n_wells = 5, 40, 12, 9
+    rows = rng.normal(size=(blocks, cap, D)).astype(np.float32)
+    rows[:, :, 0] = rng.integers(0, n_wells, (blocks, cap))
+    counts = np.array([40, 0, 17, 33, 1], np.int64)
+    d_rows, d_counts = dev(rows), dev(counts)
+    one_mean, one_count = plate.well_means(d_rows, d_counts, n_wells)
+    agg = plate.WellAggregator(n_wells, D)
+    agg.add(d_rows[:2].contiguous(), d_counts[:2].contiguous())
+    agg.add(d_rows[2:].contiguous(), d_counts[2:].contiguous())
+    mean, count = agg.finalize()
+    np.testing.assert_allclose(host(mean), host(one_mean), rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(host(count), host(one_count))
+    valid = np.concatenate([rows[b, :counts[b]] for b in range(blocks)]).astype(np.float64)
+    ids, ref = o_norm.well_mean(valid, valid[:, 0].astype(int))
+    np.testing.assert_allclose(host(mean)[ids], ref, rtol=1e-12)
