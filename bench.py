@@ -325,20 +325,19 @@ def gpu_arm(args):
                                            field_base=g * chunk_fields, out=mine)
             n = int(total.item())
             rows_seen[0] += n
-            blk = (all_rows[g * world:(g + 1) * world], all_counts[g * world:(g + 1) * world])
-            gatherer.gather(mine, n, out=blk)
-            well_agg.add(*blk)                              # per-well sums of this chunk, still on the side stream
+            gatherer.gather(mine, n, out=(all_rows[g * world:(g + 1) * world], all_counts[g * world:(g + 1) * world]))
 
     def finish_plate():
-        with torch.cuda.stream(agg_stream):
-            res = well_agg.finalize()
+        # Per-well sums run after the last field: measured at N = 8, folding them into the side
+        # stream chunk by chunk slowed the field kernels by more (0.755 -> 0.794 ms per launch)
+        # than the shorter tail gained (profiles/README.md).
         torch.cuda.current_stream().wait_stream(agg_stream)
-        return res
+        well_agg.reset()
+        well_agg.add(all_rows, all_counts)
+        return well_agg.finalize()
 
     def aggregate_all():
         rows_seen[0] = 0
-        with torch.cuda.stream(agg_stream):
-            well_agg.reset()
         for g in range(n_chunks):
             gather_chunk(g)
         return finish_plate()
@@ -383,8 +382,6 @@ def gpu_arm(args):
         t_begin.record()
         rows_seen[0] = 0
         chunks_done = 0
-        with torch.cuda.stream(agg_stream):
-            well_agg.reset()
         for i in range(args.steps):
             step(i, evs[i])
             if args.steps == n_slots and (i + 1) % slots_per_chunk == 0 and chunks_done < n_chunks:
