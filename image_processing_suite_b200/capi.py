@@ -57,6 +57,8 @@ PROTOTYPES = {
     "ips_well_sums_reset": (i, [p, sz, i, i, p]),
     "ips_well_sums_add": (i, [p, p, i64, p, sz, i, i, p]),
     "ips_well_sums_finalize": (i, [p, sz, p, p, i, i, p]),
+    "ips_cell_crops_workspace_bytes": (sz, [i, i]),
+    "ips_cell_crops": (i, [p, p, p, p, i, i, p, p, p, p, sz, i, i, i, i, i, p]),
     "ips_mad_robustize": (i, [p, p, p, i, i, p]),
     "ips_double_sigmoid_abs": (i, [p, p, i64, i, C.c_double, p]),
     "ips_pack_rows_workspace_bytes": (sz, [i]),

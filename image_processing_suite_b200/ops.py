@@ -391,3 +391,34 @@ def double_sigmoid_abs(x, k=3, alpha=2.3538):
         y = torch.empty_like(x)
         capi.call("ips_double_sigmoid_abs", _ptr(x), _ptr(y), x.numel(), int(k), float(alpha), _stream(dev))
     return y
+
+
+# ---- cell crops ----------------------------------------------------------------------------
+def cell_crops(corrected, labels, ints, n_objects, box=200, max_crops=None):
+    """Centroid-centred masked crops of every object, min-max scaled to uint8 per crop and
+    channel (Cellpose_GPU_s3fs.py:149-182, :34-43).
+
+    corrected [F][C][H][W] float32, labels [F][H][W] int32, ints [F][Nmax][6] / n_objects [F]
+    from object_stats / field_fused.  Returns dict: ``crops`` uint8 [F][max_crops][C][box][box],
+    ``kept`` int32 [F][max_crops][3] (label, yc, xc), ``n_kept`` int32 [F].
+    """
+    _check(corrected, "corrected", torch.float32, 4)
+    dev = corrected.device
+    F, Cn, H, W = corrected.shape
+    _check(labels, "labels", torch.int32, 3, dev)
+    _check(ints, "ints", torch.int32, 3, dev)
+    _check(n_objects, "n_objects", torch.int32, 1, dev)
+    if tuple(labels.shape) != (F, H, W) or ints.shape[0] != F or ints.shape[2] != 6 or n_objects.shape[0] != F:
+        raise ValueError("shape mismatch between corrected, labels and object rows")
+    n_max = ints.shape[1]
+    if max_crops is None:
+        max_crops = n_max
+    with torch.cuda.device(dev):
+        crops = torch.empty((F, max_crops, Cn, box, box), dtype=torch.uint8, device=dev)
+        kept = torch.zeros((F, max_crops, 3), dtype=torch.int32, device=dev)
+        n_kept = torch.empty((F,), dtype=torch.int32, device=dev)
+        ws = _workspace(capi.call("ips_cell_crops_workspace_bytes", F, n_max), dev)
+        capi.call("ips_cell_crops", _ptr(corrected), _ptr(labels), _ptr(ints), _ptr(n_objects), int(box),
+                  int(max_crops), _ptr(crops), _ptr(n_kept), _ptr(kept), _ptr(ws), ws.numel(), n_max, F, Cn, H, W,
+                  _stream(dev))
+    return {"crops": crops, "kept": kept, "n_kept": n_kept}

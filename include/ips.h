@@ -181,6 +181,23 @@ int ips_well_sums_add(const float* rows, const int32_t* well, int64_t N, void* w
 int ips_well_sums_finalize(const void* ws, size_t ws_bytes, double* mean_out, int32_t* count_out,
                            int D, int n_wells, ips_stream_t stream);
 
+/* ---- centroid-centred masked cell crops, scaled to 8 bit -----------------------------------
+ * Replaces the per-cell loop of Cellpose_GPU_s3fs.py:149-182 and scale_to_8bit (:34-43).
+ * corrected [F][C][H][W] float32 (the illumination-corrected planes, K1's `corrected`),
+ * labels [F][H][W] int32, ints / n_objects: the rows of ips_object_stats / ips_field_fused.
+ * For every object in label order: centroid truncated to integers (exact), dropped when the
+ * box x box window leaves the image, every channel of the window masked by `label == id`,
+ * min-max scaled to [0, 255] in float32 and truncated (a constant window gives zeros).
+ * crops [F][max_crops][C][box][box] uint8; kept [F][max_crops][3] int32 = label, yc, xc;
+ * n_kept [F] = number of objects that passed the edge test (only the first max_crops are
+ * written).  box even, box <= H, W.
+ */
+size_t ips_cell_crops_workspace_bytes(int F, int Nmax);
+int ips_cell_crops(const float* corrected, const int32_t* labels, const int32_t* ints,
+                   const int32_t* n_objects, int box, int max_crops, uint8_t* crops, int32_t* n_kept,
+                   int32_t* kept, void* ws, size_t ws_bytes, int Nmax, int F, int C, int H, int W,
+                   ips_stream_t stream);
+
 /* ---- robust-z normalisation of well profiles and the double sigmoid -------------------------
  * Replaces  pycytominer normalize(method="mad_robustize", samples=<DMSO wells>)
  *           Normalize_CP_ami.py:137-142, Pycyto_pertime.py:84-89:

@@ -21,4 +21,4 @@ Pinning status (see DESIGN.md "Oracle"):
     north_star-only, or lives in CellProfiler 4.2.8 / pycytominer, neither vendored).
     The restatements follow SURVEY.md section 8c.
 """
-from . import preprocess, object_stats, illum, lanczos, qc, cosine, normalize  # noqa: F401
+from . import preprocess, object_stats, illum, lanczos, qc, cosine, normalize, crops  # noqa: F401

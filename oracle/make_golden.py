@@ -190,6 +190,19 @@ def main():
         cases[f"{name}_triu"] = v
         cases[f"{name}_mean"] = np.array(np.mean(v) if len(v) > 0 else np.nan)
     np.savez_compressed(os.path.join(OUT, "cosine.npz"), **cases)
+
+    # ---- crops: the reference's own scale_to_8bit (Cellpose_GPU_s3fs.py:34-43) ------------
+    cp = _load("Cellpose_GPU_s3fs.py", "ref_cellpose")
+    cases = {}
+    for name, shape in {"a": (40, 40), "b": (24, 36), "const": (16, 16), "tiny": (3, 5)}.items():
+        img = rng.uniform(0.0, 9000.0, shape).astype(np.float32)
+        img[rng.random(shape) < 0.6] = 0.0                 # masked-out pixels of a crop are zeros
+        if name == "const":
+            img[:] = 123.5
+        cases[f"{name}_in"] = img
+        cases[f"{name}_out"] = cp.scale_to_8bit(img)
+    cases["box_size"] = np.array(cp.BOX_SIZE)
+    np.savez_compressed(os.path.join(OUT, "crops.npz"), **cases)
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)))

@@ -95,3 +95,12 @@ def test_cosine_matches_sklearn(golden_dir, case):
         assert m == pytest.approx(ref, rel=1e-12, abs=1e-15)
         n = x.shape[0]
         assert cosine.triu_sum_closed_form(x) * 2 / (n * (n - 1)) == pytest.approx(ref, rel=1e-10, abs=1e-14)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "const", "tiny"])
+def test_scale_to_8bit_matches_reference(golden_dir, case):
+    from oracle import crops
+    g = _load(golden_dir, "crops.npz")
+    out = crops.scale_to_8bit(g[f"{case}_in"])
+    assert out.dtype == np.uint8
+    np.testing.assert_array_equal(out, g[f"{case}_out"])
