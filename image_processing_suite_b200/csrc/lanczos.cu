@@ -126,8 +126,9 @@ lanczos_v_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
 // is converted once), then each thread accumulates its outputs tap by tap from shared memory in
 // exactly the same order (same __dmul_rn / __dadd_rn sequence, so the results are identical).
 constexpr int LZ_TX = 128;   // outputs along the filtered axis (h pass) / columns (v pass) per block
-constexpr int LZ_RH = 4;     // rows per block in the horizontal pass
+constexpr int LZ_RH = 8;     // rows per block in the horizontal pass
 constexpr int LZ_RV = 8;     // output rows per block in the vertical pass
+constexpr int LZ_SPAN_ITERS = 3;   // the horizontal pass stages spans of up to LZ_SPAN_ITERS * LZ_TX pixels
 
 __global__ void __launch_bounds__(LZ_TX)
 lanczos_h_staged_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
@@ -142,16 +143,29 @@ lanczos_h_staged_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ 
   const int lo = bounds[2 * xo0];
   const int hi = bounds[2 * (xo1 - 1)] + bounds[2 * (xo1 - 1) + 1];
   const int span = hi - lo;
+  // every load of the block's input span is issued before the first conversion (the loop below
+  // is fully unrolled: LZ_RH x LZ_SPAN_ITERS independent loads in flight per thread)
+  uint16_t v[LZ_RH][LZ_SPAN_ITERS];
 #pragma unroll
   for (int r = 0; r < LZ_RH; ++r) {
     const int y = y0 + r;
     const uint16_t* src = in + ((size_t)p * H + (y < H ? y : H - 1)) * W + lo;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < span; i += LZ_TX) lz_s[r * span_max + i] = (double)src[i];
+#pragma unroll
+    for (int j = 0; j < LZ_SPAN_ITERS; ++j) {
+      const int i = threadIdx.x + j * LZ_TX;
+      v[r][j] = i < span ? src[i] : (uint16_t)0;
+    }
   }
+#pragma unroll
+  for (int r = 0; r < LZ_RH; ++r)
+#pragma unroll
+    for (int j = 0; j < LZ_SPAN_ITERS; ++j) {
+      const int i = threadIdx.x + j * LZ_TX;
+      if (i < span) lz_s[r * span_max + i] = (double)v[r][j];
+    }
   // the weights of the block's outputs are one contiguous piece of the table
   const double* kblk = kk + (size_t)xo0 * ksize;
-#pragma unroll 4
+#pragma unroll 8
   for (int idx = threadIdx.x; idx < (xo1 - xo0) * ksize; idx += LZ_TX) kk_s[idx] = kblk[idx];
   __syncthreads();
   const int xx = xo0 + threadIdx.x;
@@ -274,7 +288,7 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
     uint16_t* h_out = need_v ? tmp : out;
     const int span_max = lanczos_span_max(c, outW, LZ_TX);
     const size_t smem = ((size_t)LZ_RH * span_max + (size_t)LZ_TX * c.ksize) * sizeof(double);
-    if (smem <= LZ_SMEM_LIMIT && (H + LZ_RH - 1) / LZ_RH <= 65535) {
+    if (smem <= LZ_SMEM_LIMIT && span_max <= LZ_SPAN_ITERS * LZ_TX && (H + LZ_RH - 1) / LZ_RH <= 65535) {
       IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_h_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       lanczos_h_staged_kernel<<<dim3((outW + LZ_TX - 1) / LZ_TX, (H + LZ_RH - 1) / LZ_RH, C), LZ_TX, smem, st>>>(
           in, h_out, db, dk, c.ksize, H, W, outW, span_max);
