@@ -158,3 +158,72 @@ def test_feature_extraction_and_illum_estimate_scripts(tmp_path):
         np.testing.assert_allclose(sub.Intensity_MeanIntensity_ER, e_f[:, 2 + 5 + 1], rtol=1e-5)
         np.testing.assert_allclose(sub.Intensity_StdIntensity_DNA, e_f[:, 2 + 2], rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(sub.Intensity_IntegratedIntensity_DNA, e_f[:, 2 + 0], rtol=1e-5)
+
+
+@pytest.mark.parametrize("qc_drop", [False, True])
+def test_normalize_script_matches_pandas_and_oracle(tmp_path, monkeypatch, qc_drop):
+    """Normalize_CP_ami drop-in on a local 'bucket': per-well means and robust-z scores against a
+    pure pandas / oracle restatement of the same steps (pycytominer parts: parity unpinned)."""
+    require_gpu()
+    from functools import reduce
+    from image_processing_suite_b200.scripts import Normalize_CP_ami as nz, storage
+    from oracle import normalize as o_norm
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    s3 = storage.client()
+    rng = np.random.default_rng(7)
+    wells = [f"{r}{c:02d}" for r in "ABCD" for c in range(1, 7)]
+    rows_img, tabs = [], {"Nuclei": [], "Cells": [], "Cytoplasm": []}
+    image_number = 0
+    for w in wells:
+        for site in range(1, 4 if w != "B03" else 3):          # one well has fewer sites
+            image_number += 1
+            bad = image_number % 11 == 0
+            rows_img.append({"ImageNumber": image_number, "Metadata_Well": w, "Metadata_Site": site, "Metadata_Plate": "P1",
+                             "Count_Nuclei": int(rng.integers(5, 30)), "ImageQC_Blurry": int(bad),
+                             "ExecutionTime_X": 1.5, "Intensity_Mean": rng.normal(0.3, 0.05)})
+            for name in tabs:
+                for obj in range(int(rng.integers(3, 7))):
+                    tabs[name].append({"ImageNumber": image_number, "ObjectNumber": obj + 1,
+                                       "AreaShape_Area": int(rng.integers(300, 1500)),
+                                       "Intensity_MeanIntensity_DNA": rng.normal(0.2, 0.03),
+                                       "Location_Center_X": rng.uniform(0, 2160)})
+    s3.put_object(Bucket="b", Key="exp/P1/24h/Image.csv", Body=pd.DataFrame(rows_img).to_csv(index=False).encode())
+    for name, rows in tabs.items():
+        s3.put_object(Bucket="b", Key=f"exp/P1/24h/{name}.csv", Body=pd.DataFrame(rows).to_csv(index=False).encode())
+    pm = pd.DataFrame({"Metadata_Well": wells, "Metadata_Plate": "P1", "Metadata_ConcLevel": 1,
+                       "Metadata_Compound": ["dmso" if i % 4 == 0 else f"cmp{i}" for i in range(len(wells))]})
+    s3.put_object(Bucket="b", Key="exp/Plate_P1_PlateMap.csv", Body=pm.to_csv(index=False).encode())
+    keys = nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", "mean", False, qc_drop, s3)
+    assert keys == ["norm/P1/Normalized_features_24h.csv"]
+    got = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key=keys[0])["Body"].read()))
+    # ---- the same steps in pandas + the oracle's mad_robustize -------------------------------
+    image_df = pd.DataFrame(rows_img)
+    failing = image_df.loc[image_df.filter(like="ImageQC_").any(axis=1), "ImageNumber"]
+    per_table = []
+    for name, prefix in nz.TABLE_PREFIX.items():
+        df = image_df if name == "Image" else pd.DataFrame(tabs[name]).merge(
+            image_df[["ImageNumber", "Metadata_Well", "Metadata_Site"]], on="ImageNumber", how="left")
+        if qc_drop:
+            df = df[~df["ImageNumber"].isin(failing)]
+        keep = {"Metadata_Well", "Metadata_Site"} if qc_drop else {"Metadata_Well"}
+        df = df.drop(columns=[c for c in df.columns if c == "ImageNumber" or (c.startswith("Metadata") and c not in keep)
+                              or any(s in c for s in nz.DROP_SUBSTRINGS)])
+        df = df.rename(columns=lambda x: prefix + x if not x.startswith("Metadata_") else x)
+        if qc_drop:
+            sc = df.groupby("Metadata_Well")["Metadata_Site"].nunique()
+            df = df.merge((sc.max() / sc).rename("scaling_factor"), on="Metadata_Well")
+            ints = [c for c in df.select_dtypes(include="integer").columns if not c.startswith("Metadata")]
+            df[ints] = df[ints].multiply(df["scaling_factor"], axis=0)
+            df = df.drop(columns=["scaling_factor", "Metadata_Site"])
+        per_table.append(df.groupby("Metadata_Well", as_index=False).agg("mean"))
+    merged = reduce(lambda l, r: pd.merge(l, r, on="Metadata_Well", how="outer"), per_table)
+    pm2 = pm[["Metadata_Compound", "Metadata_ConcLevel", "Metadata_Well", "Metadata_Plate"]].copy()
+    pm2["Metadata_Compound"] = pm2["Metadata_Compound"].str.upper()
+    merged = pm2.merge(merged, on="Metadata_Well", how="inner")
+    feats = [c for c in merged.columns if "Metadata" not in c]
+    z = o_norm.mad_robustize(merged[feats].to_numpy(float), (merged["Metadata_Compound"] == "DMSO").to_numpy())
+    assert list(got.columns) == [c for c in merged.columns if c not in feats] + ["Metadata_Timepoint"] + feats
+    assert list(got["Metadata_Well"]) == list(merged["Metadata_Well"])
+    np.testing.assert_allclose(got[feats].to_numpy(float), z, rtol=1e-9, atol=1e-9)
+    with pytest.raises(ValueError, match="no GPU kernel"):
+        nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", "median", False, qc_drop, s3)

@@ -76,3 +76,12 @@ def test_feature_extraction_schema_helpers():
     assert (r.AreaShape_Center_X, r.Location_Center_Y) == (6.25, 3.5)
     text = fr.to_csv(index=False).splitlines()[1]
     assert text.startswith("7,3,12,5,2,9,6,")               # integer columns without a decimal point
+
+
+def test_normalize_cli_flags_match_the_reference():
+    from image_processing_suite_b200.scripts import Normalize_CP_ami
+    f = _flags(Normalize_CP_ami.build_parser())          # Normalize_CP_ami.py:156-165
+    assert set(f) == {"--bucket_name", "--base_folder", "--plates", "--times", "--DMSO", "--output_bucket",
+                      "--output_prefix", "--well_agg_func", "--no_time_subFolder", "--qc_drop"}
+    assert f["--DMSO"] == (False, "DMSO") and f["--well_agg_func"] == (False, "mean")
+    assert f["--qc_drop"] == (False, False) and f["--plates"][0] and not f["--times"][0]
