@@ -5,7 +5,6 @@ elementwise z-max (MaxProjection.py:45) runs in ips_preprocess_fused on the GPU.
 the CLI loop uses: all channels of one field (C x Z planes) in a single fused launch.
 """
 import argparse
-import csv
 import io
 import logging
 import posixpath
@@ -33,8 +32,7 @@ def read_csv_from_s3(bucket_name, file_key, s3_client=None):
     """Data-set CSV with ';' or ',' sniffed from the first KiB (MaxProjection.py:24-31)."""
     s3 = s3_client or storage.client()
     content = s3.get_object(Bucket=bucket_name, Key=file_key)['Body'].read().decode('utf-8')
-    dialect = csv.Sniffer().sniff(content[:1024], delimiters=";,")
-    return pd.read_csv(StringIO(content), sep=dialect.delimiter)
+    return pd.read_csv(StringIO(content), sep=storage.sniff_delimiter(content))
 
 
 def _fetch(image_key, bucket_name, s3_client):

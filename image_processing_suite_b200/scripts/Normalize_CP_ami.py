@@ -18,7 +18,6 @@ does not pin pycytominer and has no test for them).
 Only --well_agg_func mean has a GPU kernel; any other value is refused (no CPU fallback).
 """
 import argparse
-import csv
 import logging
 from functools import reduce
 from io import StringIO
@@ -38,8 +37,7 @@ DROP_SUBSTRINGS = ['ExecutionTime', 'ModuleError', 'URL']
 def read_csv_from_s3(bucket_name, file_key, s3):
     logger.info(f"Reading CSV from s3://{bucket_name}/{file_key}")
     content = s3.get_object(Bucket=bucket_name, Key=file_key)['Body'].read().decode('utf-8')
-    dialect = csv.Sniffer().sniff(content[:1024], delimiters=";,")
-    return pd.read_csv(StringIO(content), sep=dialect.delimiter)
+    return pd.read_csv(StringIO(content), sep=storage.sniff_delimiter(content))
 
 
 def well_mean_gpu(df):

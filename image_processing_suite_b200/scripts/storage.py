@@ -96,3 +96,16 @@ def resource():
         return LocalClient(root)
     import boto3
     return boto3.resource("s3")
+
+
+def sniff_delimiter(text):
+    """';' or ',' as the reference's readers decide it: csv.Sniffer over the first KiB
+    (MaxProjection.py:29-30, Normalize_CP_ami.py:25-26); when the sniffer cannot decide (wide
+    tables whose first KiB holds less than two full lines) the header line's own count decides."""
+    import csv
+    sample = text[:1024]
+    try:
+        return csv.Sniffer().sniff(sample, delimiters=";,").delimiter
+    except csv.Error:
+        header = text.split("\n", 1)[0]
+        return ";" if header.count(";") > header.count(",") else ","

@@ -227,3 +227,50 @@ def test_normalize_script_matches_pandas_and_oracle(tmp_path, monkeypatch, qc_dr
     np.testing.assert_allclose(got[feats].to_numpy(float), z, rtol=1e-9, atol=1e-9)
     with pytest.raises(ValueError, match="no GPU kernel"):
         nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", "median", False, qc_drop, s3)
+
+
+def test_feature_select_cosine_script(tmp_path, monkeypatch):
+    """The cosine drop-in with an identity feature selection: double sigmoid and per-group mean
+    cosine (all groups in one kernel call) against scikit-learn, group by group."""
+    require_gpu()
+    from sklearn.metrics.pairwise import cosine_similarity
+    from image_processing_suite_b200.scripts import Feature_select_cosine_ami as fs, storage
+    from oracle import normalize as o_norm
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    s3 = storage.client()
+    rng = np.random.default_rng(12)
+    rows = []
+    for plate in ("P1", "P2"):
+        for tp in ("24h", "48h"):
+            frame = []
+            for comp, reps in (("DMSO", 6), ("CMP1", 4), ("CMP2", 1), ("CMP3", 3)):
+                for r in range(reps):
+                    d = {"Metadata_Compound": comp, "Metadata_ConcLevel": 1 + (r % 2 if comp == "CMP1" else 0),
+                         "Metadata_Well": f"{comp}{r}", "Metadata_Plate": plate, "Metadata_Timepoint": tp}
+                    d.update({f"DNA_f{j}": rng.normal(0, 3) for j in range(40)})
+                    frame.append(d)
+            df = pd.DataFrame(frame)
+            df.loc[2, "DNA_f3"] = np.nan
+            s3.put_object(Bucket="b", Key=f"exp/{plate}/Normalized_features_{tp}.csv", Body=df.to_csv(index=False).encode())
+            rows.append(df)
+    s3.put_object(Bucket="b", Key="exp/P1/sub/Normalized_features_x.csv", Body=b"ignored: deeper than the plate folder")
+    ident = lambda profiles, features, **kw: profiles
+    sims = fs.concatenate_normalized_csv_from_s3("b", ["P1", "P2"], "exp", False, "out", "res", "EXP", 0.5, 0.9,
+                                                 feature_select=ident, s3=s3)
+    allrows = pd.concat(rows, ignore_index=True)
+    feats = [c for c in allrows.columns if "Metadata" not in c]
+    allrows[feats] = np.abs(o_norm.double_sigmoid(allrows[feats].to_numpy(float)))
+    dsig = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key="res/EXP_CP_features_selected_allTimes_dSig.csv")["Body"].read()))
+    np.testing.assert_allclose(dsig[feats].to_numpy(float), allrows[feats].to_numpy(float), rtol=1e-12, equal_nan=True)
+    expected = []
+    for key in allrows[fs.GROUP_KEYS].drop_duplicates().values:
+        grp = allrows[(allrows.Metadata_Compound == key[0]) & (allrows.Metadata_Timepoint == key[1]) &
+                      (allrows.Metadata_ConcLevel == key[2])]
+        s = cosine_similarity(grp[feats].fillna(0))
+        v = s[np.triu_indices_from(s, k=1)]
+        expected.append(np.mean(v) if len(v) else np.nan)
+    assert list(sims[fs.GROUP_KEYS].itertuples(index=False, name=None)) == \
+        [tuple(k) for k in allrows[fs.GROUP_KEYS].drop_duplicates().values]
+    np.testing.assert_allclose(sims["average_cosine_similarity"].to_numpy(), np.asarray(expected), atol=1e-5, equal_nan=True)
+    saved = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key="res/EXP_Average_cosine_similarity.csv")["Body"].read()))
+    assert len(saved) == len(sims)

@@ -85,3 +85,15 @@ def test_normalize_cli_flags_match_the_reference():
                       "--output_prefix", "--well_agg_func", "--no_time_subFolder", "--qc_drop"}
     assert f["--DMSO"] == (False, "DMSO") and f["--well_agg_func"] == (False, "mean")
     assert f["--qc_drop"] == (False, False) and f["--plates"][0] and not f["--times"][0]
+
+
+def test_feature_select_cosine_cli_flags_match_the_reference():
+    from image_processing_suite_b200.scripts import Feature_select_cosine_ami as fs
+    f = _flags(fs.build_parser())                          # Feature_select_cosine_ami.py:169-178
+    assert f == {"--bucket_name": (True, None), "--base_folder": (True, None), "--plates": (True, None),
+                 "--exp": (True, None), "--na_cutoff": (False, 0.5), "--corr_3hold": (False, 0.9),
+                 "--per_time": (False, False), "--output_bucket": (True, None), "--output_prefix": (True, None),
+                 "--local_dir": (False, "temp_data")}
+    assert (fs.k, fs.alpha) == (3, 2.3538)
+    with pytest.raises(ImportError, match="pycytominer"):
+        fs._default_feature_select()
