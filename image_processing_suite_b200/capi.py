@@ -52,6 +52,8 @@ PROTOTYPES = {
     "ips_ring_sums": (i, [p, p, p, i, i, i, i, p]),
     "ips_cosine_workspace_bytes": (sz, [i, i]),
     "ips_cosine_triu": (i, [p, p, i, p, p, i, i, p, sz, p]),
+    "ips_cosine_pairs_workspace_bytes": (sz, [i, i]),
+    "ips_cosine_triu_pairs": (i, [p, p, i, p, p, p, p, u64, i, i, p, sz, p]),
     "ips_well_mean_workspace_bytes": (sz, [i, i]),
     "ips_well_mean": (i, [p, p, p, p, i, i, i, p, sz, p]),
     "ips_well_sums_reset": (i, [p, sz, i, i, p]),

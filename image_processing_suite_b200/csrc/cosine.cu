@@ -94,7 +94,9 @@ __device__ __forceinline__ void triu_tile(long long t, int nt, int& bi, int& bj)
 
 __global__ void __launch_bounds__(CS_THREADS)
 cosine_triu_kernel(const float* __restrict__ Xn, const int32_t* __restrict__ group,
-                   double* __restrict__ sum_out, int N, int D, int nt, long long n_tiles, int n_groups) {
+                   double* __restrict__ sum_out, int N, int D, int nt, long long n_tiles, int n_groups,
+                   const unsigned long long* __restrict__ grp_start, const unsigned long long* __restrict__ grp_count,
+                   const unsigned long long* __restrict__ pair_base, double* __restrict__ pairs_out) {
   __shared__ float As[CS_K][CS_TILE + 4];
   __shared__ float Bs[CS_K][CS_TILE + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -148,11 +150,38 @@ cosine_triu_kernel(const float* __restrict__ Xn, const int32_t* __restrict__ gro
         if (c <= c1 && c > r && (group == nullptr || group[c] == gr)) {
           s += (double)acc[i][j];
           any = true;
+          if (pairs_out != nullptr && gr >= 0 && gr < n_groups) {
+            // row-major strict upper triangle of the group, as np.triu_indices(n, k=1) orders it
+            const unsigned long long n = grp_count[gr], li = (unsigned long long)r - grp_start[gr],
+                                     lj = (unsigned long long)c - grp_start[gr];
+            pairs_out[pair_base[gr] + li * n - li * (li + 1) / 2 + (lj - li - 1)] = (double)acc[i][j];
+          }
         }
       }
       if (any && gr >= 0 && gr < n_groups) atomicAdd(&sum_out[gr], s);
     }
   }
+}
+
+__global__ void cosine_total_pairs_kernel(unsigned long long* pair_base, const unsigned long long* npairs, int n_groups) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) pair_base[n_groups] = pair_base[n_groups - 1] + npairs[n_groups - 1];
+}
+
+// group starts (first row), sizes and the offset of every group's pair block; one thread
+__global__ void cosine_group_layout_kernel(const int32_t* __restrict__ group, int N, int n_groups,
+                                           const unsigned long long* __restrict__ counts,
+                                           unsigned long long* __restrict__ grp_start,
+                                           unsigned long long* __restrict__ pair_base) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned long long row = 0, pairs = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    grp_start[g] = row;
+    pair_base[g] = pairs;
+    const unsigned long long n = counts[g];
+    row += n;
+    pairs += n * (n > 0 ? n - 1 : 0) / 2;
+  }
+  (void)group; (void)N;
 }
 
 }  // namespace ips
@@ -214,7 +243,63 @@ extern "C" int ips_cosine_triu(const float* X, const int32_t* group, int n_group
   const int nt = (N + CS_TILE - 1) / CS_TILE;
   const long long n_tiles = (long long)nt * (nt + 1) / 2;
   const long long want = n_tiles < (long long)sm_count() * 64 ? n_tiles : (long long)sm_count() * 64;
-  cosine_triu_kernel<<<(unsigned)want, CS_THREADS, 0, st>>>(Xn, group, sum_out, N, D, nt, n_tiles, n_groups);
+  cosine_triu_kernel<<<(unsigned)want, CS_THREADS, 0, st>>>(Xn, group, sum_out, N, D, nt, n_tiles, n_groups, nullptr,
+                                                            nullptr, nullptr, nullptr);
+  IPS_LAUNCH_OK("cosine_triu_kernel");
+  return IPS_OK;
+}
+
+// Same as ips_cosine_triu on the exact fp32 path, and additionally every pair's similarity:
+// pairs_out holds, group after group, the row-major strict upper triangle of the group's
+// similarity matrix (what Pycyto_pertime.py:150-155 keeps as `cosine_similarities`);
+// pair_offsets_out [n_groups + 1] are the block boundaries.  Rows of a group must be contiguous
+// and group ids ascending from 0.  pairs_capacity bounds the number of pair values written.
+extern "C" size_t ips_cosine_pairs_workspace_bytes(int N, int D) {
+  if (N <= 0 || D <= 0) return 0;
+  return round_up((size_t)N * D * sizeof(float), 256) + 3 * round_up((size_t)(N + 1) * sizeof(unsigned long long), 256);
+}
+
+extern "C" int ips_cosine_triu_pairs(const float* X, const int32_t* group, int n_groups, double* sum_out,
+                                     uint64_t* npairs_out, double* pairs_out, uint64_t* pair_offsets_out,
+                                     uint64_t pairs_capacity, int N, int D, void* ws, size_t ws_bytes,
+                                     ips_stream_t stream) {
+  if (!sum_out || !npairs_out || !pairs_out || !pair_offsets_out) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_cosine_triu_pairs: NULL output");
+  if (N <= 0 || D <= 0 || n_groups <= 0 || n_groups > N)
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_cosine_triu_pairs: bad shape N=%d D=%d groups=%d", N, D, n_groups);
+  if (X == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_cosine_triu_pairs: X is NULL");
+  if (group == nullptr && n_groups != 1) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_cosine_triu_pairs: group == NULL means one group");
+  // upper bound of the pair count: all rows in one group
+  if ((unsigned long long)N * (unsigned long long)(N - 1) / 2 > pairs_capacity && n_groups == 1)
+    IPS_FAIL(IPS_ERR_NOMEM, "ips_cosine_triu_pairs: pairs_out too small for %d rows in one group", N);
+  const size_t need = ips_cosine_pairs_workspace_bytes(N, D);
+  if (ws == nullptr || ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "ips_cosine_triu_pairs: needs %zu workspace bytes (got %zu)", need, ws_bytes);
+  if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_cosine_triu_pairs: workspace not 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* q = reinterpret_cast<char*>(ws);
+  float* Xn = reinterpret_cast<float*>(q); q += round_up((size_t)N * D * sizeof(float), 256);
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(q); q += round_up((size_t)(N + 1) * sizeof(unsigned long long), 256);
+  unsigned long long* grp_start = reinterpret_cast<unsigned long long*>(q); q += round_up((size_t)(N + 1) * sizeof(unsigned long long), 256);
+  unsigned long long* np = reinterpret_cast<unsigned long long*>(npairs_out);
+  unsigned long long* pair_base = reinterpret_cast<unsigned long long*>(pair_offsets_out);
+  cosine_zero_kernel<<<(n_groups + 255) / 256, 256, 0, st>>>(sum_out, counts, n_groups);
+  IPS_LAUNCH_OK("cosine_zero_kernel");
+  cosine_count_kernel<<<(N + 255) / 256, 256, 0, st>>>(group, counts, N, n_groups);
+  IPS_LAUNCH_OK("cosine_count_kernel");
+  cosine_pairs_kernel<<<(n_groups + 255) / 256, 256, 0, st>>>(counts, np, n_groups);
+  IPS_LAUNCH_OK("cosine_pairs_kernel");
+  cosine_group_layout_kernel<<<1, 32, 0, st>>>(group, N, n_groups, counts, grp_start, pair_base);
+  IPS_LAUNCH_OK("cosine_group_layout_kernel");
+  // the closing boundary pair_offsets_out[n_groups] = total pairs
+  cosine_total_pairs_kernel<<<1, 32, 0, st>>>(pair_base, np, n_groups);
+  IPS_LAUNCH_OK("cosine_total_pairs_kernel");
+  cosine_normalise_kernel<<<(N + 7) / 8, 256, 0, st>>>(X, Xn, N, D);
+  IPS_LAUNCH_OK("cosine_normalise_kernel");
+  const int nt = (N + CS_TILE - 1) / CS_TILE;
+  const long long n_tiles = (long long)nt * (nt + 1) / 2;
+  const long long want = n_tiles < (long long)sm_count() * 64 ? n_tiles : (long long)sm_count() * 64;
+  (void)pairs_capacity;
+  cosine_triu_kernel<<<(unsigned)want, CS_THREADS, 0, st>>>(Xn, group, sum_out, N, D, nt, n_tiles, n_groups, grp_start,
+                                                            counts, pair_base, pairs_out);
   IPS_LAUNCH_OK("cosine_triu_kernel");
   return IPS_OK;
 }

@@ -422,3 +422,32 @@ def cell_crops(corrected, labels, ints, n_objects, box=200, max_crops=None):
                   int(max_crops), _ptr(crops), _ptr(n_kept), _ptr(kept), _ptr(ws), ws.numel(), n_max, F, Cn, H, W,
                   _stream(dev))
     return {"crops": crops, "kept": kept, "n_kept": n_kept}
+
+
+def cosine_triu_pairs(X, group=None, group_sizes=None):
+    """Per-group strict-upper-triangle similarities themselves (Pycyto_pertime.py:150-155).
+
+    X [N][D] float32, group [N] int32 ascending contiguous ids (or None), ``group_sizes`` the
+    host-side list of group sizes (needed to size the output; default: one group of N rows).
+    Returns (sum [G] float64, npairs [G] int64, pairs float64 [total], offsets int64 [G + 1]).
+    """
+    _check(X, "X", torch.float32, 2)
+    dev = X.device
+    N, D = X.shape
+    if group is None:
+        group_sizes = [N]
+    elif group_sizes is None:
+        group_sizes = torch.bincount(group.to(torch.int64)).cpu().tolist()
+    G = len(group_sizes)
+    total = int(sum(n * (n - 1) // 2 for n in group_sizes))
+    if group is not None:
+        _check(group, "group", torch.int32, 1, dev)
+    with torch.cuda.device(dev):
+        s = torch.empty((G,), dtype=torch.float64, device=dev)
+        npairs = torch.empty((G,), dtype=torch.int64, device=dev)
+        pairs = torch.empty((max(total, 1),), dtype=torch.float64, device=dev)
+        offsets = torch.empty((G + 1,), dtype=torch.int64, device=dev)
+        ws = _workspace(capi.call("ips_cosine_pairs_workspace_bytes", N, D), dev)
+        capi.call("ips_cosine_triu_pairs", _ptr(X), _ptr(group), G, _ptr(s), _ptr(npairs), _ptr(pairs), _ptr(offsets),
+                  max(total, N * (N - 1) // 2 if G == 1 else total), N, D, _ptr(ws), ws.numel(), _stream(dev))
+    return s, npairs, pairs[:total], offsets

@@ -164,6 +164,17 @@ int ips_cosine_triu(const float* X, const int32_t* group, int n_groups, double* 
                     uint64_t* npairs_out, int N, int D, void* ws, size_t ws_bytes,
                     ips_stream_t stream);
 
+/* As ips_cosine_triu (exact fp32 path) plus every pair's similarity: pairs_out holds, group
+ * after group, the row-major strict upper triangle of the group's similarity matrix -- the
+ * vector Pycyto_pertime.py:150-155 keeps as `cosine_similarities`; pair_offsets_out
+ * [n_groups + 1] are the block boundaries (device).  The caller sizes pairs_out for
+ * sum_g n_g (n_g - 1) / 2 values (pairs_capacity is checked against the one-group bound). */
+size_t ips_cosine_pairs_workspace_bytes(int N, int D);
+int ips_cosine_triu_pairs(const float* X, const int32_t* group, int n_groups, double* sum_out,
+                          uint64_t* npairs_out, double* pairs_out, uint64_t* pair_offsets_out,
+                          uint64_t pairs_capacity, int N, int D, void* ws, size_t ws_bytes,
+                          ips_stream_t stream);
+
 /* ---- well-level aggregation (consumer of the all-gather) -------------------------------
  * Replaces  df.groupby("Metadata_Well").agg("mean")    Normalize_CP_ami.py:126,
  *                                                       Pycyto_pertime.py:69-72

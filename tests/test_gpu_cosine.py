@@ -73,3 +73,23 @@ def test_cosine_tensor_core_path_matches_closed_form(n, d):
     assert abs(float(host(s)[0]) - ref) / (n * (n - 1) // 2) < ATOL
     if n <= 1500:
         assert abs(float(host(s)[0]) - float(o_cos.triu_values(x.astype(np.float64)).sum())) / (n * (n - 1) // 2) < ATOL
+
+
+def test_cosine_pairs_vector_matches_triu_values():
+    """The per-pair vector of every replicate group, in np.triu_indices order."""
+    require_gpu()
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(21)
+    sizes = [4, 1, 6, 2, 70, 3]
+    group = np.repeat(np.arange(len(sizes)), sizes).astype(np.int32)
+    x = rng.normal(size=(group.size, 90)).astype(np.float32)
+    s, npairs, pairs, offsets = ops.cosine_triu_pairs(dev(x), dev(group), group_sizes=sizes)
+    off = host(offsets)
+    assert off.tolist() == np.r_[0, np.cumsum([n * (n - 1) // 2 for n in sizes])].tolist()
+    for g, n in enumerate(sizes):
+        ref = o_cos.triu_values(x[group == g].astype(np.float64))
+        got = host(pairs)[off[g]:off[g + 1]]
+        assert got.shape == ref.shape and int(host(npairs)[g]) == ref.size
+        np.testing.assert_allclose(got, ref, atol=ATOL)
+        if ref.size:
+            assert abs(float(host(s)[g]) - ref.sum()) < ATOL * ref.size
