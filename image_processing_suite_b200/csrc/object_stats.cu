@@ -153,6 +153,16 @@ object_stats_scan_kernel(const int32_t* __restrict__ labels, const uint16_t* __r
   // register set would (measured, profiles/README.md).  All-background rows are not loaded.
   if (__any_sync(OA_FULL, fg != 0u)) {
     for (int c = 0; c < C; ++c) {
+      // next channel's rows towards L2 while this one is folded (as in field_fused.cu)
+      if (VEC && c + 1 < C && row_need != 0u) {
+#pragma unroll
+        for (int r = 0; r < K3_ROWS; ++r) {
+          if (!((row_need >> r) & 1u) || y0 + r >= H) continue;
+          const size_t off = (size_t)(c + 1) * plane + (size_t)(y0 + r) * W + x0;
+          if ((lane & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + off));
+          if (HAS_ILLUM && (lane & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(illum + off));
+        }
+      }
       k3_load_chan<HAS_ILLUM, VEC>(cur, mp, illum, (size_t)c * plane, y0, x0, H, W, row_need, pol_stream, pol_keep);
       consume(cur, c);
     }
