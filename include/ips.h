@@ -156,8 +156,11 @@ int ips_ring_sums(const double* spec_interleaved, double* mag_out, double* pow_o
  * Replaces  cosine_similarity(features) -> triu(k=1) -> mean
  *           Feature_select_cosine_ami.py:145-149, Pycyto_pertime.py:132-140
  * X [N][D] float32 (NaN already replaced by 0).  Rows are L2-normalised (zero rows stay
- * zero).  group [N] int32 (rows of one group must be contiguous) or NULL (one group).
- * sum_out[g] float64 = sum over i<j in group g of cos(i, j); npairs_out[g] = #pairs.
+ * zero).  group [N] int32, ids ascending from 0 with the rows of a group contiguous, or NULL
+ * (one group).  sum_out[g] float64 = sum over i<j in group g of cos(i, j); npairs_out[g] =
+ * #pairs.  Groups are evaluated with exact fp32 products on CUDA cores; a single group of at
+ * least 1024 rows (group == NULL) runs on the tensor cores -- tcgen05.mma on a bf16 hi/lo
+ * split of the normalised rows, fp32 accumulators in TMEM, |error| ~ 1e-7 per cosine.
  */
 size_t ips_cosine_workspace_bytes(int N, int D);
 int ips_cosine_triu(const float* X, const int32_t* group, int n_groups, double* sum_out,
