@@ -8,6 +8,7 @@ schemas, with the per-image arithmetic routed through libips.so (CUDA, no CPU fa
                                   (the CellProfiler command line of Feature_extraction_opt.py:166-167)
     python -m image_processing_suite_b200.scripts.Normalize_CP_ami --bucket_name ...    (Normalize_CP_ami.py)
     python -m image_processing_suite_b200.scripts.Feature_select_cosine_ami ...         (Feature_select_cosine_ami.py)
+    python -m image_processing_suite_b200.scripts.Pycyto_pertime --bucket_name ...      (Pycyto_pertime.py)
     python -m image_processing_suite_b200.scripts.Illumination_estimate ...             (new: writes {ch}_illum.npy)
 
 Storage: the reference talks to S3 through boto3.  ``storage.client()`` returns a boto3

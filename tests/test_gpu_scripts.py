@@ -274,3 +274,66 @@ def test_feature_select_cosine_script(tmp_path, monkeypatch):
     np.testing.assert_allclose(sims["average_cosine_similarity"].to_numpy(), np.asarray(expected), atol=1e-5, equal_nan=True)
     saved = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key="res/EXP_Average_cosine_similarity.csv")["Body"].read()))
     assert len(saved) == len(sims)
+
+
+def test_pycyto_pertime_script(tmp_path, monkeypatch):
+    """Pycyto_pertime drop-in with an identity feature selection against pandas / oracle /
+    scikit-learn on the same tables (per-pair similarity vectors included)."""
+    require_gpu()
+    from functools import reduce
+    from sklearn.metrics.pairwise import cosine_similarity
+    from image_processing_suite_b200.scripts import Pycyto_pertime as pp, storage
+    from oracle import normalize as o_norm
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    s3 = storage.client()
+    rng = np.random.default_rng(31)
+    img_rows, tabs = [], {"Nuclei": [], "Cells": [], "Cytoplasm": []}
+    n = 0
+    for wi in range(12):
+        comp = "DMSO" if wi % 3 == 0 else f"CMP{wi % 4}"
+        for site in (1, 2):
+            n += 1
+            img_rows.append({"ImageNumber": n, "Metadata_Plate": "Plate_1", "Metadata_Site": site, "Metadata_Well": f"W{wi:02d}",
+                             "Metadata_Timepoint": "24h", "Metadata_Compound": comp, "Metadata_ConcLevel": 1 + wi % 2,
+                             "Count_Nuclei": int(rng.integers(10, 40)), "FileName_DNA": "x.tiff",
+                             "Granularity_1": rng.normal(5, 1)})
+            for name in tabs:
+                for _ in range(int(rng.integers(3, 6))):
+                    tabs[name].append({"ImageNumber": n, "AreaShape_Area": int(rng.integers(300, 900)),
+                                       "Intensity_Mean_DNA": rng.normal(0.2, 0.05), "Texture_1": rng.normal(1, 0.3)})
+    s3.put_object(Bucket="b", Key="proj/Plate_1/24h/Image.csv", Body=pd.DataFrame(img_rows).to_csv(index=False).encode())
+    for name, rows in tabs.items():
+        s3.put_object(Bucket="b", Key=f"proj/Plate_1/24h/{name}.csv", Body=pd.DataFrame(rows).to_csv(index=False).encode())
+    ident = lambda profiles, features, **kw: profiles
+    res = pp.concatenate_csv_from_s3("b", ["24h"], "proj/Plate_1", "out", "res", feature_select=ident, s3=s3)
+    selected, averaged, sims = res["24h"]
+    # ---- the same steps in pandas -------------------------------------------------------------
+    image = pd.DataFrame(img_rows)
+    objs = {k: pd.DataFrame(v).merge(image[["ImageNumber"] + pp.IMAGE_META], on="ImageNumber", how="left")
+            .drop(["ImageNumber", "Metadata_Site", "Metadata_ConcLevel"], axis=1) for k, v in tabs.items()}
+    image = image.drop(["ImageNumber"], axis=1)
+    image = image.drop(columns=[c for c in image.columns
+                                if not pd.api.types.is_numeric_dtype(image[c]) and not c.startswith("Metadata")])
+    g = {k: v.groupby(pp.KEYS, as_index=False).mean() for k, v in objs.items()}
+    image = image.groupby(pp.KEYS, as_index=False).mean().rename(columns=lambda x: "Image_" + x if x not in pp.IMAGE_META else x)
+    merged = reduce(lambda l, r: pd.merge(l, r, on=pp.KEYS, how="outer"), [g["Cells"], g["Nuclei"], image, g["Cytoplasm"]])
+    feats = [c for c in merged.columns if "Metadata" not in c]
+    z = np.abs(o_norm.double_sigmoid(o_norm.mad_robustize(merged[feats].to_numpy(float), (merged.Metadata_Compound == "DMSO").to_numpy())))
+    assert [c for c in selected.columns if "Metadata" not in c] == feats
+    np.testing.assert_allclose(selected[feats].to_numpy(float), z, rtol=1e-8, atol=1e-10)
+    merged[feats] = z
+    k = 0
+    for key in merged[["Metadata_Compound", "Metadata_Timepoint", "Metadata_ConcLevel"]].drop_duplicates().values:
+        grp = merged[(merged.Metadata_Compound == key[0]) & (merged.Metadata_ConcLevel == key[2])]
+        smat = cosine_similarity(grp[feats + ["Metadata_Site"]].fillna(0)) if False else cosine_similarity(
+            grp.drop(columns=["Metadata_Plate", "Metadata_Well", "Metadata_Site", "Metadata_Compound", "Metadata_Timepoint",
+                              "Metadata_ConcLevel"]).fillna(0))
+        v = smat[np.triu_indices_from(smat, k=1)]
+        assert averaged.loc[k, "Metadata_compound_code"] == key[0]
+        np.testing.assert_allclose(sims.loc[k, "cosine_similarities"], v, atol=1e-5)
+        if len(v):
+            assert abs(averaged.loc[k, "average_cosine_similarity"] - v.mean()) < 1e-5
+        else:
+            assert np.isnan(averaged.loc[k, "average_cosine_similarity"])
+        k += 1
+    assert k == len(averaged)

@@ -97,3 +97,10 @@ def test_feature_select_cosine_cli_flags_match_the_reference():
     assert (fs.k, fs.alpha) == (3, 2.3538)
     with pytest.raises(ImportError, match="pycytominer"):
         fs._default_feature_select()
+
+
+def test_pycyto_pertime_cli_flags_match_the_reference():
+    from image_processing_suite_b200.scripts import Pycyto_pertime
+    f = _flags(Pycyto_pertime.build_parser())              # Pycyto_pertime.py:179-184
+    assert f == {"--bucket_name": (True, None), "--base_folder": (True, None), "--times": (True, None),
+                 "--output_bucket": (True, None), "--output_prefix": (True, None), "--local_dir": (False, "temp_data")}
