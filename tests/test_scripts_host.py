@@ -1,7 +1,6 @@
 """Host-side logic of the drop-in scripts (no GPU): flags, path rules, storage stand-in,
 TIFF round trip, CSV sniffing -- mirrored from the reference scripts."""
 import io
-import os
 
 import numpy as np
 import pytest

@@ -1,6 +1,5 @@
 """Small driver for ncu captures: a few launches of K1 / K3 / fused on a 16-field batch."""
 import sys
-import numpy as np
 import torch
 sys.path.insert(0, ".")
 import bench
