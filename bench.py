@@ -181,7 +181,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     illum = synth.make_illum(C_, H_, W_, seed=0).astype(np.float64)
     # a few distinct fields, cycled; generation is outside the timed region
-    n_distinct = min(cores, 8)
+    n_distinct = max(1, min(cores, 8, args.ref_fields))
     fields = host_fields(n_distinct, H_, W_, seed=0)
     # size one step: time one full field on one thread, then pick rows so that
     # (warmup + steps) steps, each `cores` band-fields wide, fit the budget
@@ -537,6 +537,7 @@ def main():
     ap.add_argument("--e2e-fields", type=int, default=256)
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=120.0)
+    ap.add_argument("--ref-fields", type=int, default=8, help="distinct synthetic fields the reference arm cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: native libraries (NCCL prints its version banner to
