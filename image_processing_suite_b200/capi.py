@@ -61,6 +61,13 @@ PROTOTYPES = {
     "ips_well_sums_finalize": (i, [p, sz, p, p, i, i, p]),
     "ips_cell_crops_workspace_bytes": (sz, [i, i]),
     "ips_cell_crops": (i, [p, p, p, p, i, i, p, p, p, p, sz, i, i, i, i, i, p]),
+    "ips_tiff_rows_per_strip": (i, [i, i]),
+    "ips_tiff_lzw_bound": (sz, [sz]),
+    "ips_tiff_file_bound": (sz, [i, i, i]),
+    "ips_tiff_encode_workspace_bytes": (sz, [i, i, i, i]),
+    "ips_tiff_lzw_encode_u16": (i, [p, i, i, i, i, p, sz, p, p, sz, p]),
+    "ips_tiff_lzw_decode": (i, [p, p, p, p, p, p, i, p, p]),
+    "ips_tiff_fix_u16": (i, [p, i64, i, i, i, p]),
     "ips_mad_robustize": (i, [p, p, p, i, i, p]),
     "ips_double_sigmoid_abs": (i, [p, p, i64, i, C.c_double, p]),
     "ips_pack_rows_workspace_bytes": (sz, [i]),

@@ -451,3 +451,77 @@ def cosine_triu_pairs(X, group=None, group_sizes=None):
         capi.call("ips_cosine_triu_pairs", _ptr(X), _ptr(group), G, _ptr(s), _ptr(npairs), _ptr(pairs), _ptr(offsets),
                   max(total, N * (N - 1) // 2 if G == 1 else total), N, D, _ptr(ws), ws.numel(), _stream(dev))
     return s, npairs, pairs[:total], offsets
+
+
+# ---- K7: TIFF strip codec -----------------------------------------------------------------
+def tiff_rows_per_strip(H, W):
+    """Pillow's strip height for an H x W 16-bit plane."""
+    return int(capi.call("ips_tiff_rows_per_strip", int(H), int(W)))
+
+
+def tiff_lzw_encode(planes, rows_per_strip=None):
+    """uint16 planes [P][H][W] (device) -> (files uint8 [P][file_cap] on the device, file_bytes
+    int64 [P] on the host).  files[p, :file_bytes[p]] is the complete LZW TIFF of plane p, the
+    bytes ``img.save(buf, format='TIFF', compression='tiff_lzw')`` (Image_re-binning.py:19-21)
+    produces for the same pixels."""
+    _check(planes, "planes", torch.uint16, 3)
+    P, H, W = planes.shape
+    if H <= 0 or W <= 0:
+        raise ValueError("empty planes")
+    dev = planes.device
+    rps = tiff_rows_per_strip(H, W) if rows_per_strip is None else int(rows_per_strip)
+    if rps <= 0:
+        raise ValueError("rows_per_strip must be positive")
+    cap = int(capi.call("ips_tiff_file_bound", H, W, rps))
+    with torch.cuda.device(dev):
+        files = torch.empty((P, cap), dtype=torch.uint8, device=dev)
+        nbytes = torch.zeros((P,), dtype=torch.int64, device=dev)
+        if P:
+            ws = _workspace(capi.call("ips_tiff_encode_workspace_bytes", P, H, W, rps), dev)
+            capi.call("ips_tiff_lzw_encode_u16", _ptr(planes), P, H, W, rps, _ptr(files), cap, _ptr(nbytes),
+                      _ptr(ws), ws.numel(), _stream(dev))
+        host = nbytes.cpu()
+    if P and int(host.min()) <= 0:
+        raise capi.IpsError(-6, "ips_tiff_lzw_encode_u16: a file did not fit its slot")
+    return files, host
+
+
+def tiff_lzw_decode(src, src_off, src_bytes, dst, dst_off, dst_bytes):
+    """LZW strips src[src_off[s] : +src_bytes[s]] -> dst[dst_off[s] : +dst_bytes[s]] (uint8 views,
+    device).  The descriptor arrays are host sequences.  Returns the per-strip status (host
+    int32 tensor; 0 = ok).  Replaces the strip decoding behind Image.open / imageio.imread
+    (Image_re-binning.py:17, MaxProjection.py:39)."""
+    _check(src, "src", torch.uint8, 1)
+    _check(dst, "dst", torch.uint8, 1, src.device)
+    n = len(src_off)
+    if not (len(src_bytes) == len(dst_off) == len(dst_bytes) == n):
+        raise ValueError("descriptor arrays differ in length")
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.int32)
+    so = torch.as_tensor(list(src_off), dtype=torch.int64)
+    sb = torch.as_tensor(list(src_bytes), dtype=torch.int64)
+    do = torch.as_tensor(list(dst_off), dtype=torch.int64)
+    db = torch.as_tensor(list(dst_bytes), dtype=torch.int64)
+    if int(so.min()) < 0 or int(sb.min()) < 0 or int((so + sb).max()) > src.numel():
+        raise ValueError("a source strip lies outside src")
+    if int(do.min()) < 0 or int(db.min()) < 0 or int((do + db).max()) > dst.numel():
+        raise ValueError("a destination strip lies outside dst")
+    if int(sb.max()) >= 2 ** 32 or int(db.max()) >= 2 ** 32:
+        raise ValueError("strips of 4 GiB or more are not supported")
+    dev = src.device
+    with torch.cuda.device(dev):
+        desc64 = torch.stack([so, do]).to(dev)
+        desc32 = torch.stack([sb, db]).to(torch.uint32).to(dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+        capi.call("ips_tiff_lzw_decode", _ptr(src), _ptr(desc64[0]), _ptr(desc32[0]), _ptr(dst), _ptr(desc64[1]),
+                  _ptr(desc32[1]), n, _ptr(status), _stream(dev))
+        return status.cpu()
+
+
+def tiff_fix_u16(img, predictor=1, byteswap=False):
+    """In place on uint16 rows [..., W]: byte swap, then undo horizontal differencing (Predictor 2)."""
+    _check(img, "img", torch.uint16)
+    W = img.shape[-1]
+    rows = img.numel() // W if W else 0
+    capi.call("ips_tiff_fix_u16", _ptr(img), rows, W, int(predictor), int(bool(byteswap)), _stream(img.device))
+    return img

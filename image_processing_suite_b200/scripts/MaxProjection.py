@@ -10,7 +10,6 @@ import logging
 import posixpath
 from io import StringIO
 
-import numpy as np
 import pandas as pd
 
 from . import storage, tiffio
@@ -36,26 +35,31 @@ def read_csv_from_s3(bucket_name, file_key, s3_client=None):
 
 
 def _fetch(image_key, bucket_name, s3_client):
-    return tiffio.decode(s3_client.get_object(Bucket=bucket_name, Key=image_key)['Body'].read())
+    return s3_client.get_object(Bucket=bucket_name, Key=image_key)['Body'].read()
+
+
+def _load_group(keys, bucket_name, s3_client):
+    """Encoded planes of one channel -> uint16 CUDA tensor [Z][H][W] (TIFF strips decoded on the
+    device); ValueError on a shape mismatch like MaxProjection.py:42-43."""
+    try:
+        planes = tiffio.load_planes([_fetch(k, bucket_name, s3_client) for k in keys])
+    except ValueError as e:
+        if "shape mismatch" in str(e):
+            raise ValueError(f"Image shape mismatch in group: {keys}")
+        raise
+    return planes
 
 
 def _project(stack_czhw):
-    """[C][Z][H][W] uint16 (host) -> [C][H][W] uint16 via the CUDA kernel."""
-    import torch
+    """[C][Z][H][W] uint16 (device) -> [C][H][W] uint16 (host) via the CUDA kernel."""
     from .. import ops
-    raw = torch.from_numpy(np.ascontiguousarray(stack_czhw[None])).cuda()
-    return ops.preprocess_fused(raw, None, bin=1, want_binned=False)["maxproj"][0].cpu().numpy()
+    return ops.preprocess_fused(stack_czhw[None].contiguous(), None, bin=1, want_binned=False)["maxproj"][0].cpu().numpy()
 
 
 def max_projection(image_group, bucket_name, s3_client):
     """Max-project the planes of one channel and upload the result (MaxProjection.py:33-52).
     Raises ValueError when the planes differ in shape, like the reference (:42-43)."""
-    images = [_fetch(k, bucket_name, s3_client) for k in image_group]
-    if not all(img.shape == images[0].shape for img in images):
-        raise ValueError(f"Image shape mismatch in group: {image_group}")
-    if images[0].dtype != np.uint16:
-        raise ValueError("max_projection expects 16-bit images, got %s" % images[0].dtype)
-    max_proj = _project(np.stack(images)[None])[0]
+    max_proj = _project(_load_group(image_group, bucket_name, s3_client)[None])[0]
     s3_client.upload_fileobj(io.BytesIO(tiffio.encode(max_proj)), bucket_name, modify_imagepath(image_group[0]))
 
 
@@ -63,22 +67,20 @@ def max_project_chunk(groups, bucket_name, s3_client):
     """groups: list over channels of lists over planes of keys.  One launch for the field;
     channels whose planes fail to load or mismatch are reported like the reference does
     (logged, the other channels still go through).  Returns the number written."""
+    import torch
     stacks, ok = [], []
     for j, group in enumerate(groups):
         try:
-            images = [_fetch(k, bucket_name, s3_client) for k in group]
-            if not all(img.shape == images[0].shape for img in images):
-                raise ValueError(f"Image shape mismatch in group: {group}")
-            stacks.append(np.stack(images))
+            stacks.append(_load_group(group, bucket_name, s3_client))
             ok.append(j)
         except Exception as e:
             logger.error(f"Error processing group {j}: {e}")
     written = 0
     by_shape = {}
     for j, st in zip(ok, stacks):
-        by_shape.setdefault(st.shape, []).append((j, st))
+        by_shape.setdefault(tuple(st.shape), []).append((j, st))
     for items in by_shape.values():
-        proj = _project(np.stack([st for _, st in items]))
+        proj = _project(torch.stack([st for _, st in items]))
         for (j, _), mp in zip(items, proj):
             s3_client.upload_fileobj(io.BytesIO(tiffio.encode(mp)), bucket_name, modify_imagepath(groups[j][0]))
             written += 1

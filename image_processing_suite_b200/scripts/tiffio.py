@@ -39,3 +39,143 @@ def encode(arr, compression=None):
 def write(path, arr, compression=None):
     with open(path, "wb") as f:
         f.write(encode(arr, compression))
+
+
+# ---- device codec (K7) ---------------------------------------------------------------------
+# The strips of 16-bit single-sample TIFFs are decoded and LZW-encoded on the GPU
+# (ips_tiff_lzw_decode / ips_tiff_lzw_encode_u16): compressed bytes are what crosses PCIe.
+# Anything outside that layout (tiles, other compressions, PNG/JPEG inputs the reference also
+# accepts, Image_re-binning.py:40) raises Unsupported and the caller uses decode() above.
+class Unsupported(ValueError):
+    pass
+
+
+_TYPE_FMT = {1: "B", 3: "H", 4: "I", 16: "Q"}
+
+
+def parse(data):
+    """First IFD of a classic TIFF -> dict; raises Unsupported for anything the device codec
+    does not read."""
+    import struct
+    if len(data) < 8 or data[:2] not in (b"II", b"MM"):
+        raise Unsupported("not a TIFF")
+    e = "<" if data[:2] == b"II" else ">"
+    magic, ifd = struct.unpack_from(e + "HI", data, 2)
+    if magic != 42:
+        raise Unsupported("BigTIFF / unknown magic %d" % magic)
+    if ifd + 2 > len(data):
+        raise Unsupported("IFD outside the file")
+    (n,) = struct.unpack_from(e + "H", data, ifd)
+    if ifd + 2 + 12 * n > len(data):
+        raise Unsupported("IFD outside the file")
+    tags = {}
+    for k in range(n):
+        tag, typ, cnt = struct.unpack_from(e + "HHI", data, ifd + 2 + 12 * k)
+        fmt = _TYPE_FMT.get(typ)
+        if fmt is None:
+            continue
+        size = struct.calcsize(fmt) * cnt
+        at = ifd + 10 + 12 * k
+        if size > 4:
+            (at,) = struct.unpack_from(e + "I", data, at)
+        if at + size > len(data):
+            raise Unsupported("tag %d outside the file" % tag)
+        tags[tag] = struct.unpack_from(e + "%d%s" % (cnt, fmt), data, at)
+    if 256 not in tags or 257 not in tags or 273 not in tags or 279 not in tags:
+        raise Unsupported("not a stripped TIFF")
+    if 322 in tags or 324 in tags:
+        raise Unsupported("tiled TIFF")
+    w, h = int(tags[256][0]), int(tags[257][0])
+    info = dict(width=w, height=h, big_endian=(e == ">"), bits=tags.get(258, (1,))[0],
+                samples=tags.get(277, (1,))[0], compression=tags.get(259, (1,))[0],
+                predictor=tags.get(317, (1,))[0], offsets=list(tags[273]), counts=list(tags[279]),
+                rows_per_strip=min(int(tags.get(278, (h,))[0]), h), sample_format=tags.get(339, (1,))[0])
+    if info["bits"] != 16 or info["samples"] != 1 or info["sample_format"] != 1:
+        raise Unsupported("device codec reads 16-bit unsigned single-sample images")
+    if info["compression"] not in (1, 5) or info["predictor"] not in (1, 2):
+        raise Unsupported("compression %d / predictor %d" % (info["compression"], info["predictor"]))
+    if w <= 0 or h <= 0 or info["rows_per_strip"] <= 0:
+        raise Unsupported("empty image")
+    n_strips = -(-h // info["rows_per_strip"])
+    if len(info["offsets"]) != n_strips or len(info["counts"]) != n_strips:
+        raise Unsupported("strip tables do not match the image height")
+    for o, c in zip(info["offsets"], info["counts"]):
+        if o + c > len(data):
+            raise Unsupported("strip outside the file")
+    return info
+
+
+def decode_to_device(files, device=None):
+    """list of TIFF byte strings of equal shape -> uint16 CUDA tensor [P][H][W].
+    Raises Unsupported (before touching the GPU) when any file is outside the device codec's
+    layout, ValueError when shapes differ or a strip is corrupt."""
+    import torch
+    from .. import ops
+    infos = [parse(f) for f in files]
+    if not infos:
+        raise ValueError("no files")
+    h, w = infos[0]["height"], infos[0]["width"]
+    if any((i["height"], i["width"]) != (h, w) for i in infos):
+        raise ValueError("Image shape mismatch")
+    dev = torch.device(device if device is not None else "cuda")
+    plane = h * w * 2
+    base, total = [], 0
+    for f in files:
+        base.append(total)
+        total += (len(f) + 15) // 16 * 16
+    host = torch.empty((total,), dtype=torch.uint8).pin_memory() if total else torch.empty((0,), dtype=torch.uint8)
+    hv = host.numpy()
+    for b, f in zip(base, files):
+        hv[b:b + len(f)] = np.frombuffer(f, dtype=np.uint8)
+    src = host.to(dev, non_blocking=True)
+    out = torch.empty((len(files), h, w), dtype=torch.uint16, device=dev)
+    dst = out.view(torch.uint8).reshape(-1)
+    so, sb, do, db = [], [], [], []
+    for p, (b, i) in enumerate(zip(base, infos)):
+        rps = i["rows_per_strip"]
+        for s, (o, c) in enumerate(zip(i["offsets"], i["counts"])):
+            rows = min(rps, h - s * rps)
+            d0, dn = p * plane + s * rps * w * 2, rows * w * 2
+            if i["compression"] == 5:
+                so.append(b + o); sb.append(c); do.append(d0); db.append(dn)
+            else:
+                if c < dn:
+                    raise ValueError("uncompressed strip %d of file %d is short" % (s, p))
+                dst[d0:d0 + dn] = src[b + o:b + o + dn]
+    if so:
+        status = ops.tiff_lzw_decode(src, so, sb, dst, do, db)
+        if int(status.max()) != 0:
+            bad = int(torch.nonzero(status)[0])
+            raise ValueError("LZW strip %d is damaged (status %d)" % (bad, int(status[bad])))
+    for p, i in enumerate(infos):
+        if i["big_endian"] or i["predictor"] == 2:
+            ops.tiff_fix_u16(out[p], predictor=i["predictor"], byteswap=i["big_endian"])
+    return out
+
+
+def encode_lzw_from_device(planes, rows_per_strip=None):
+    """uint16 CUDA tensor [P][H][W] -> list of P LZW TIFF byte strings, the bytes Pillow's
+    save(format='TIFF', compression='tiff_lzw') writes for the same pixels."""
+    from .. import ops
+    files, nbytes = ops.tiff_lzw_encode(planes, rows_per_strip)
+    if not len(nbytes):
+        return []
+    host = files[:, :int(nbytes.max())].cpu().numpy()
+    return [host[p, :int(n)].tobytes() for p, n in enumerate(nbytes)]
+
+
+def load_planes(files, device=None):
+    """list of encoded 16-bit images -> uint16 CUDA tensor [P][H][W]: the device codec when every
+    file is a TIFF it reads, otherwise decode() on the host and one copy.  ValueError when the
+    planes differ in shape or are not 16-bit."""
+    import torch
+    try:
+        return decode_to_device(files, device)
+    except Unsupported:
+        pass
+    images = [decode(f) for f in files]
+    if not all(img.shape == images[0].shape for img in images):
+        raise ValueError("Image shape mismatch")
+    if any(img.dtype != np.uint16 or img.ndim != 2 for img in images):
+        raise ValueError("expected single-plane 16-bit images, got %s %s" % (images[0].dtype, images[0].shape))
+    return torch.from_numpy(np.ascontiguousarray(np.stack(images))).to(device if device is not None else "cuda")

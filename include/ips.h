@@ -212,6 +212,40 @@ int ips_cell_crops(const float* corrected, const int32_t* labels, const int32_t*
                    int32_t* kept, void* ws, size_t ws_bytes, int Nmax, int F, int C, int H, int W,
                    ips_stream_t stream);
 
+/* ---- K7: TIFF strip codec (the file edge of the re-binning and max-projection scripts) ------
+ * Replaces  img.save(buf, format='TIFF', compression='tiff_lzw')   Image_re-binning.py:19-21
+ *      and  Image.open(...) / imageio.imread(...) of LZW strips     Image_re-binning.py:17,
+ *                                                                   MaxProjection.py:39.
+ * The codec is libtiff's (inside Pillow): TIFF 6.0 LZW, MSB-first 9..12-bit codes, ClearCode
+ * first, reset at code 4094 or when the ratio check (every 10000 bytes) fails.  The encoder
+ * follows that policy exactly: the files are byte-identical to Pillow 12.2 / libtiff 4.7.
+ *
+ * ips_tiff_rows_per_strip   Pillow's strip height: min(65536 / (2 W), H), at least 1.
+ * ips_tiff_lzw_bound        largest LZW stream of a strip of that many bytes.
+ * ips_tiff_file_bound       largest file of one H x W uint16 plane (multiple of 16).
+ * ips_tiff_lzw_encode_u16   planes [P][H][W] uint16 -> files [P][file_cap] bytes, each a complete
+ *                           little-endian single-IFD TIFF of file_bytes[p] bytes (0 = did not
+ *                           fit; cannot happen with file_cap >= ips_tiff_file_bound).
+ * ips_tiff_lzw_decode       n_strips LZW streams src[src_off[s] .. +src_bytes[s]) -> exactly
+ *                           dst_bytes[s] bytes at dst[dst_off[s]]; status[s] = 0, or 1 truncated,
+ *                           2 corrupt, 3 pre-6.0 bit order (the remainder is zero-filled).
+ *                           The five descriptor arrays are device pointers.
+ * ips_tiff_fix_u16          in place on rows x W samples: byte swap (big-endian files), then
+ *                           running sum modulo 2^16 along the row when predictor == 2.
+ */
+int ips_tiff_rows_per_strip(int H, int W);
+size_t ips_tiff_lzw_bound(size_t strip_bytes);
+size_t ips_tiff_file_bound(int H, int W, int rows_per_strip);
+size_t ips_tiff_encode_workspace_bytes(int P, int H, int W, int rows_per_strip);
+int ips_tiff_lzw_encode_u16(const uint16_t* planes, int P, int H, int W, int rows_per_strip,
+                            uint8_t* files, size_t file_cap, uint64_t* file_bytes, void* ws,
+                            size_t ws_bytes, ips_stream_t stream);
+int ips_tiff_lzw_decode(const uint8_t* src, const uint64_t* src_off, const uint32_t* src_bytes,
+                        uint8_t* dst, const uint64_t* dst_off, const uint32_t* dst_bytes,
+                        int n_strips, int32_t* status, ips_stream_t stream);
+int ips_tiff_fix_u16(uint16_t* img, int64_t rows, int W, int predictor, int byteswap,
+                     ips_stream_t stream);
+
 /* ---- robust-z normalisation of well profiles and the double sigmoid -------------------------
  * Replaces  pycytominer normalize(method="mad_robustize", samples=<DMSO wells>)
  *           Normalize_CP_ami.py:137-142, Pycyto_pertime.py:84-89:

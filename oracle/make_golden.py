@@ -203,10 +203,44 @@ def main():
         cases[f"{name}_out"] = cp.scale_to_8bit(img)
     cases["box_size"] = np.array(cp.BOX_SIZE)
     np.savez_compressed(os.path.join(OUT, "crops.npz"), **cases)
+    tiff_golden()
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def tiff_golden():
+    """File-level fixtures of Image_re-binning.process_image_in_memory: the TIFF bytes that go in
+    and the LZW TIFF bytes the reference returns (own generator: the other fixtures keep their
+    random streams)."""
+    from PIL import Image
+    _install_stubs()
+    rb = _load("Image_re-binning.py", "ref_rebin_tiff")
+    rng = np.random.default_rng(20261018)
+    cases = {}
+    specs = {"noise": (96, 128, 48, 64, None), "lzw_in": (80, 120, 40, 60, "tiff_lzw"),
+             "flat": (200, 400, 100, 200, None), "tall": (700, 60, 350, 30, "tiff_lzw"),
+             "ident": (90, 110, 90, 110, None)}
+    for name, (h, w, oh, ow, comp) in specs.items():
+        if name == "flat":
+            img = np.full((h, w), 300, np.uint16)
+            img[50:60, 100:300] = 65535
+        else:
+            img = np.clip(rng.normal(400, 40, (h, w)), 0, 65535).astype(np.uint16)
+            img[5:12, 5:25] = 65535
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, format="tiff", **({"compression": comp} if comp else {}))
+        out_bytes = rb.process_image_in_memory(buf.getvalue(), target_size=(ow, oh))
+        cases[f"{name}_in"] = np.frombuffer(buf.getvalue(), np.uint8)
+        cases[f"{name}_file"] = np.frombuffer(out_bytes, np.uint8)
+        cases[f"{name}_size"] = np.array([ow, oh])
+    cases["pillow_version"] = np.array(Image.__version__)
+    np.savez_compressed(os.path.join(OUT, "tiff_lzw.npz"), **cases)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["tiff"]:
+        os.makedirs(OUT, exist_ok=True)
+        tiff_golden()
+    else:
+        main()

@@ -1,0 +1,157 @@
+"""CPU checks of the TIFF strip codec: the oracle restatement against Pillow/libtiff and the
+golden files the reference's process_image_in_memory wrote, the host build of the very state
+machines the CUDA kernels run (csrc/tiff_lzw_core.cuh, 1-lane warp) against both, and the
+product's TIFF parser."""
+import ctypes
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import lanczos as o_lz
+from oracle import tiff_lzw as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def pil_lzw(a, **kw):
+    buf = io.BytesIO()
+    Image.fromarray(a).save(buf, format="tiff", compression="tiff_lzw", **kw)
+    return buf.getvalue()
+
+
+def images():
+    rng = np.random.default_rng(5)
+    yield "noise", np.clip(rng.normal(300, 30, (120, 200)), 0, 65535).astype(np.uint16)
+    yield "zeros", np.zeros((300, 500), np.uint16)              # ratio check resets the table early
+    yield "const", np.full((64, 64), 65535, np.uint16)
+    yield "full", rng.integers(0, 65536, (90, 333)).astype(np.uint16)   # table fills: reset at code 4094
+    yield "ramp", (np.arange(400 * 300) % 1000).reshape(300, 400).astype(np.uint16)
+    yield "one", np.array([[7]], np.uint16)
+    yield "tall", rng.integers(0, 50, (2000, 3)).astype(np.uint16)
+    yield "wide", rng.integers(0, 5, (2, 40000)).astype(np.uint16)      # stride > 64 KiB: one row per strip
+
+
+@pytest.mark.parametrize("name,img", list(images()), ids=[n for n, _ in images()])
+def test_oracle_files_equal_pillow(name, img):
+    ref = pil_lzw(img)
+    assert T.encode_tiff_lzw(img) == ref
+    np.testing.assert_array_equal(T.decode_tiff(ref), img)
+
+
+def test_oracle_reads_predictor_and_uncompressed():
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 65536, (50, 70)).astype(np.uint16)
+    np.testing.assert_array_equal(T.decode_tiff(pil_lzw(img, tiffinfo={317: 2})), img)
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, format="tiff")
+    np.testing.assert_array_equal(T.decode_tiff(buf.getvalue()), img)
+
+
+def test_oracle_reproduces_reference_files(golden_dir):
+    """The reference's own output bytes (Image_re-binning.process_image_in_memory, run by
+    oracle/make_golden.py) from the oracle's Lanczos + TIFF writer."""
+    g = np.load(os.path.join(golden_dir, "tiff_lzw.npz"))
+    for name in ("noise", "lzw_in", "flat", "tall", "ident"):
+        src = T.decode_tiff(g[f"{name}_in"].tobytes())
+        ow, oh = (int(v) for v in g[f"{name}_size"])
+        assert T.encode_tiff_lzw(o_lz.pil_resize(src, (oh, ow))) == g[f"{name}_file"].tobytes(), name
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("lzw") / "lzw_harness.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", os.path.join(ROOT, "tests", "native", "lzw_host_harness.cpp"), "-o", so],
+                   check=True)
+    h = ctypes.CDLL(so)
+    h.harness_bound.restype = ctypes.c_uint64
+    h.harness_bound.argtypes = [ctypes.c_uint64]
+    h.harness_encode.restype = ctypes.c_uint32
+    h.harness_encode.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
+    h.harness_decode.restype = ctypes.c_int
+    h.harness_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
+    return h
+
+
+def _enc(h, raw, off=0):
+    cap = h.harness_bound(len(raw))
+    out = np.zeros(cap, np.uint8)
+    src = np.zeros(len(raw) + 8, np.uint8)
+    src[off:off + len(raw)] = np.frombuffer(raw, np.uint8)
+    n = h.harness_encode(src.ctypes.data + off, len(raw), out.ctypes.data, cap)
+    assert n != 0xFFFFFFFF
+    return out[:n].tobytes()
+
+
+def _dec(h, comp, n, off=0, ooff=0):
+    out = np.full(n + 64, 0xAB, np.uint8)
+    src = np.zeros(len(comp) + 8, np.uint8)
+    src[off:off + len(comp)] = np.frombuffer(comp, np.uint8)
+    st = h.harness_decode(src.ctypes.data + off, len(comp), out.ctypes.data + ooff, n)
+    assert (out[:ooff] == 0xAB).all() and (out[ooff + n:] == 0xAB).all()      # nothing outside the strip
+    return st, out[ooff:ooff + n].tobytes()
+
+
+@pytest.mark.parametrize("name,img", list(images()), ids=[n for n, _ in images()])
+def test_kernel_state_machines_equal_pillow(harness, name, img):
+    """Every strip Pillow writes: the kernels' encoder reproduces its bytes and the kernels'
+    decoder its pixels, at every input / output alignment."""
+    info = T.parse_tiff(pil_lzw(img))
+    ref = pil_lzw(img)
+    rps = info["rps"]
+    for s, (o, c) in enumerate(zip(info["offsets"], info["counts"])):
+        raw = img[s * rps:(s + 1) * rps].tobytes()
+        for off in range(4):
+            assert _enc(harness, raw, off) == ref[o:o + c]
+            st, px = _dec(harness, ref[o:o + c], len(raw), off, (5 * off + s) % 16)
+            assert st == 0 and px == raw
+
+
+def test_kernel_decoder_reports_damage(harness):
+    rng = np.random.default_rng(8)
+    raw = np.clip(rng.normal(300, 30, 10000), 0, 65535).astype(np.uint16).tobytes()
+    comp = _enc(harness, raw)
+    st, px = _dec(harness, comp[:len(comp) // 2], len(raw))
+    assert st == 1 and px[-100:] == bytes(100)                       # truncated: remainder zero-filled
+    st, px = _dec(harness, comp, 1000)                               # fewer bytes wanted than coded: fine
+    assert st == 0 and px == raw[:1000]
+    assert _dec(harness, b"\x00\x01" + comp, 100)[0] == 3            # pre-6.0 bit order
+    assert _dec(harness, bytes(rng.integers(0, 256, 500, dtype=np.uint8)), 4000)[0] in (1, 2)
+    assert _dec(harness, b"", 16)[0] == 1
+
+
+def test_kernel_encoder_overflow_is_reported(harness):
+    raw = np.random.default_rng(9).integers(0, 256, 4096, dtype=np.uint8).tobytes()
+    out = np.zeros(1024, np.uint8)
+    src = np.frombuffer(raw, np.uint8).copy()
+    assert harness.harness_encode(src.ctypes.data, len(raw), out.ctypes.data, 1024) == 0xFFFFFFFF
+
+
+def test_product_parser_matches_oracle_and_rejects_other_layouts():
+    from image_processing_suite_b200.scripts import tiffio
+    img = np.arange(100 * 40, dtype=np.uint16).reshape(100, 40)
+    for kw in ({}, {"compression": "tiff_lzw"}, {"compression": "tiff_lzw", "tiffinfo": {317: 2}}):
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, format="tiff", **kw)
+        a, b = tiffio.parse(buf.getvalue()), T.parse_tiff(buf.getvalue())
+        assert (a["width"], a["height"], a["compression"], a["predictor"], a["rows_per_strip"]) == \
+               (b["width"], b["height"], b["compression"], b["predictor"], b["rps"])
+        assert a["offsets"] == b["offsets"] and a["counts"] == b["counts"]
+    for kw in ({"compression": "tiff_adobe_deflate"},):
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, format="tiff", **kw)
+        with pytest.raises(tiffio.Unsupported):
+            tiffio.parse(buf.getvalue())
+    buf = io.BytesIO()
+    Image.fromarray(img.astype(np.uint8)).save(buf, format="tiff")
+    with pytest.raises(tiffio.Unsupported):
+        tiffio.parse(buf.getvalue())
+    buf = io.BytesIO()
+    Image.fromarray(img.astype(np.uint8)).save(buf, format="png")
+    with pytest.raises(tiffio.Unsupported):
+        tiffio.parse(buf.getvalue())
+    with pytest.raises(tiffio.Unsupported):
+        tiffio.parse(b"II*\x00\xff\xff\xff\x7f")

@@ -6,6 +6,7 @@
 #   profile          ncu launch list of the bench step + ncu --set full of the fused kernel
 #   aux              secondary kernels (illumination, Lanczos, K1 bin sweep, K1 TMA variant)
 #   cosine [n] [d]   tensor-core cosine kernel on an n x d group
+#   tiff             device TIFF-LZW codec: parity tests, then throughput beside Pillow
 # Everything lands in gpurun_out/; copy what should be judged into profiles/.
 set -u
 mkdir -p gpurun_out
@@ -46,6 +47,12 @@ case "$what" in
     ;;
   cosine)
     timeout 600 python tools/bench_cosine.py "${2:-16384}" "${3:-3000}" | tee gpurun_out/cosine_bench.json
+    ;;
+  tiff)
+    timeout 600 python -m pytest tests/test_gpu_tiff.py tests/test_gpu_scripts.py -m gpu -q -x > gpurun_out/tiff_tests.log 2>&1
+    echo "tiff tests rc=$?"; tail -n 30 gpurun_out/tiff_tests.log
+    timeout 600 python tools/bench_tiff.py > gpurun_out/bench_tiff.jsonl 2> gpurun_out/bench_tiff.err; echo "bench rc=$?"
+    cat gpurun_out/bench_tiff.jsonl; tail -n 5 gpurun_out/bench_tiff.err
     ;;
   *) echo "unknown: $what"; exit 2 ;;
 esac
