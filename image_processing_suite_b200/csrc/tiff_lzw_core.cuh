@@ -12,7 +12,7 @@
 // Execution model: one warp per strip.  LZW is a serial state machine, so every lane runs the
 // same instruction stream on the same values (shared-memory reads broadcast, identical writes
 // collapse) and only lane 0 stores to global memory; the lanes split the work that does
-// parallelise -- clearing the 32 KB hash table and flushing decoded bytes in 16-byte vectors.
+// parallelise -- clearing the 24 KB hash table and flushing decoded bytes in 16-byte vectors.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -27,8 +27,8 @@ namespace ips_lzw {
 
 enum : int { BITS_MIN = 9, BITS_MAX = 12, CODE_CLEAR = 256, CODE_EOI = 257, CODE_FIRST = 258, CODE_MAX = 4095 };
 enum : uint32_t { CHECK_GAP = 10000 };
-enum : uint32_t { ENC_SLOTS = 8192, ENC_EMPTY = 0xFFFFFFFFu };      // open addressing, load <= 0.47
-enum : uint32_t { DEC_CODES = 4096, DEC_OBUF = 8192 };
+enum : uint32_t { ENC_SLOTS = 6144, ENC_EMPTY = 0xFFFFFFFFu };      // open addressing, load <= 0.63
+enum : uint32_t { DEC_CODES = 4096, DEC_OBUF = 4096 };
 enum : uint32_t { OVERFLOW = 0xFFFFFFFFu };
 enum : int { ST_OK = 0, ST_TRUNCATED = 1, ST_CORRUPT = 2, ST_OLD_STYLE = 3 };
 
@@ -63,31 +63,46 @@ static inline size_t encode_bound(size_t n) { return (n + n / 2 + n / 1024 + 64 
 // ------------------------------------------------------------------------------------------
 // encoder
 // ------------------------------------------------------------------------------------------
+// One byte costs one dependent chain  key -> hash -> shared-memory probe -> compare  (the warp
+// has nothing else to overlap it with), so the bookkeeping libtiff does per byte is folded into
+// quantities that only change on a table miss: incount = consumed - in_base, outcount =
+// bits emitted - bits_base, and the "code width grows / table full" tests share one compare.
+#ifdef __CUDACC__
+LZW_HD uint32_t slot_of(uint32_t key) { return __umulhi(key * 0x9E3779B1u, (uint32_t)ENC_SLOTS); }
+#else
+inline uint32_t slot_of(uint32_t key) { return (uint32_t)(((uint64_t)(key * 0x9E3779B1u) * ENC_SLOTS) >> 32); }
+#endif
+
 struct Encoder {
   uint32_t* tab;     // [ENC_SLOTS] (key << 12) | code, key = (prefix code << 8) | byte
   uint8_t* out;      // 4-byte aligned
   uint32_t cap;      // multiple of 4
   uint32_t op;       // bytes written (multiple of 4 until finish())
-  uint64_t acc;      // low nacc bits are pending output
+  uint32_t acc;      // low nacc (< 32) bits are pending output; bits above them are stale
   int nacc;
-  int nbits, maxcode, free_ent, ent;
-  uint64_t checkpoint, ratio, incount, outcount;
+  int nbits;
+  uint32_t limit;    // free_ent at which the next width change (512, 1024, 2048) or the reset (4094) happens
+  uint32_t free_ent, ent;
+  uint32_t in_base, bits_base, checkpoint, ratio;
   bool overflow;
   int lane;
 
-  LZW_HD void put(int code) {
-    acc = (acc << nbits) | (uint32_t)code;
-    nacc += nbits;
-    outcount += (uint64_t)nbits;
-    if (nacc >= 32) {
-      const uint32_t word = (uint32_t)(acc >> (nacc - 32));
-      nacc -= 32;
+  LZW_HD void put(uint32_t code) {
+    const int t = nacc + nbits;
+    if (t >= 32) {
+      const int r = t - 32;                                    // low bits of `code` that stay pending
+      const uint32_t word = (acc << (nbits - r)) | (code >> r);
+      acc = code;
+      nacc = r;
       if (op + 4 <= cap) {
         if (lane == 0) *reinterpret_cast<uint32_t*>(out + op) = bswap32(word);
         op += 4;
       } else {
         overflow = true;
       }
+    } else {
+      acc = (acc << nbits) | code;
+      nacc = t;
     }
   }
 
@@ -95,20 +110,22 @@ struct Encoder {
   LZW_HD void clear_table(const W& w) {
     w.sync();
     uint64_t* t64 = reinterpret_cast<uint64_t*>(tab);
+#pragma unroll 4
     for (uint32_t i = w.lane; i < ENC_SLOTS / 2; i += W::n) t64[i] = ~0ull;
     w.sync();
   }
 
+  // libtiff: cl_hash, ratio = incount = outcount = 0, CODE_CLEAR at the old width, 9-bit codes
   template <class W>
-  LZW_HD void reset_after_clear(const W& w) {   // libtiff: cl_hash + CODE_CLEAR + 9-bit codes
+  LZW_HD void reset(uint32_t consumed, const W& w) {
     clear_table(w);
     ratio = 0;
-    incount = 0;
-    outcount = 0;
+    in_base = consumed;
+    bits_base = op * 8u + (uint32_t)nacc;
     free_ent = CODE_FIRST;
     put(CODE_CLEAR);
     nbits = BITS_MIN;
-    maxcode = (1 << BITS_MIN) - 1;
+    limit = 1u << BITS_MIN;
   }
 
   template <class W>
@@ -120,79 +137,76 @@ struct Encoder {
     acc = 0;
     nacc = 0;
     nbits = BITS_MIN;
-    maxcode = (1 << BITS_MIN) - 1;
+    limit = 1u << BITS_MIN;
     free_ent = CODE_FIRST;
-    ent = -1;
+    ent = 0;
+    in_base = 0;
+    bits_base = 0;
     checkpoint = CHECK_GAP;
     ratio = 0;
-    incount = 0;
-    outcount = 0;
     overflow = false;
     lane = w.lane;
     clear_table(w);
   }
 
-  LZW_HD void first(uint32_t c) {      // first byte of the strip
-    put(CODE_CLEAR);
-    ent = (int)c;
-    incount++;
-  }
-
+  // c is the consumed-th byte of the strip (1-based), not the first
   template <class W>
-  LZW_HD void byte(uint32_t c, const W& w) {
-    incount++;
-    const uint32_t key = ((uint32_t)ent << 8) | c;
-    uint32_t h = (key * 0x9E3779B1u) >> 19;
+  LZW_HD void byte(uint32_t c, uint32_t consumed, const W& w) {
+    const uint32_t key = (ent << 8) | c;
+    uint32_t h = slot_of(key);
     for (;;) {
       const uint32_t s = tab[h];
       if ((s >> 12) == key) {
-        ent = (int)(s & 0xFFFu);
+        ent = s & 0xFFFu;
         return;
       }
       if (s == ENC_EMPTY) break;
-      h = (h + 1) & (ENC_SLOTS - 1);
+      h = h + 1 == ENC_SLOTS ? 0u : h + 1;
     }
     put(ent);
-    ent = (int)c;
-    tab[h] = (key << 12) | (uint32_t)free_ent;
+    ent = c;
+    tab[h] = (key << 12) | free_ent;
     free_ent++;
-    if (free_ent == CODE_MAX - 1) {
-      reset_after_clear(w);
-    } else if (free_ent > maxcode) {
-      nbits++;
-      maxcode = (1 << nbits) - 1;
-    } else if (incount >= checkpoint) {
+    if (free_ent == limit) {
+      if (limit == (uint32_t)CODE_MAX - 1) {
+        reset(consumed, w);
+      } else {
+        nbits++;
+        limit = limit == 2048u ? (uint32_t)CODE_MAX - 1 : limit << 1;
+      }
+    } else if (consumed - in_base >= checkpoint) {
+      const uint32_t incount = consumed - in_base;
+      const uint32_t outcount = op * 8u + (uint32_t)nacc - bits_base;
       checkpoint = incount + CHECK_GAP;
-      uint64_t rat;
-      if (incount > 0x007fffffull) {
+      uint32_t rat;
+      if (incount > 0x007fffffu) {
         rat = outcount >> 8;
-        rat = rat == 0 ? 0x7fffffffull : incount / rat;
+        rat = rat == 0 ? 0x7fffffffu : incount / rat;
       } else {
         rat = (incount << 8) / outcount;
       }
       if (rat <= ratio)
-        reset_after_clear(w);
+        reset(consumed, w);
       else
         ratio = rat;
     }
   }
 
   // LZWPostEncode; returns the strip's byte count or OVERFLOW
-  LZW_HD uint32_t finish() {
-    if (ent >= 0) {
+  LZW_HD uint32_t finish(bool any) {
+    if (any) {
       put(ent);
       free_ent++;
-      if (free_ent == CODE_MAX - 1) {
-        outcount = 0;
+      if (free_ent == (uint32_t)CODE_MAX - 1) {
         put(CODE_CLEAR);
         nbits = BITS_MIN;
-      } else if (free_ent > maxcode) {
+      } else if (free_ent == limit) {
         nbits++;
       }
     }
     put(CODE_EOI);
     while (nacc > 0) {
-      const uint32_t b = nacc >= 8 ? (uint32_t)(acc >> (nacc - 8)) & 0xFFu : (uint32_t)(acc << (8 - nacc)) & 0xFFu;
+      const uint32_t b = nacc >= 8 ? (acc >> (nacc - 8)) & 0xFFu : (acc << (8 - nacc)) & 0xFFu;
       nacc -= 8;
       if (op < cap) {
         if (lane == 0) out[op] = (uint8_t)b;
@@ -205,29 +219,22 @@ struct Encoder {
   }
 };
 
-// in: n bytes (any alignment); out: 4-byte aligned, cap bytes; table: ENC_SLOTS words
+// in: n < 2^28 bytes (any alignment); out: 4-byte aligned, cap bytes; table: ENC_SLOTS words
 template <class W>
 LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* table, const W& w) {
   Encoder e;
   e.begin(table, out, cap, w);
-  if (n == 0) return e.finish();
-  e.first(in[0]);
-  uint32_t i = 1;
-  // bytes up to the first 4-byte boundary of the input
-  while (i < n && ((reinterpret_cast<uintptr_t>(in + i)) & 3u)) e.byte(in[i++], w);
-  if (i + 4 <= n) {
-    uint32_t next = load_u32(in + i);                      // one word of look-ahead hides the load
-    for (; i + 4 <= n; i += 4) {
-      const uint32_t cur = next;
-      if (i + 8 <= n) next = load_u32(in + i + 4);
-      e.byte(cur & 0xFFu, w);
-      e.byte((cur >> 8) & 0xFFu, w);
-      e.byte((cur >> 16) & 0xFFu, w);
-      e.byte(cur >> 24, w);
-    }
+  if (n == 0) return e.finish(false);
+  e.put(CODE_CLEAR);
+  e.ent = in[0];
+  uint32_t next = n > 1 ? in[1] : 0u;          // one byte of look-ahead keeps the load off the chain
+#pragma unroll 1
+  for (uint32_t i = 1; i < n; ++i) {
+    const uint32_t c = next;
+    if (i + 1 < n) next = in[i + 1];
+    e.byte(c, i + 1, w);
   }
-  while (i < n) e.byte(in[i++], w);
-  return e.finish();
+  return e.finish(true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -240,7 +247,6 @@ struct Decoder {
   uint64_t acc;      // top nb bits valid
   int nb;
   uint32_t nextw;    // next 32 input bits, loaded one refill ahead
-  bool have_next;
 
   LZW_HD uint32_t fetch_word() {      // 32 bits at ip (4-byte aligned address), zero-padded past the end
     uint32_t v;
@@ -285,8 +291,8 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
   if (n_in >= 2 && in[0] == 0 && (in[1] & 1)) status = ST_OLD_STYLE;   // pre-6.0 LSB-first streams
   Decoder d;
   d.begin(in, n_in);
-  // total bits that really exist, to tell padding zeros from data
-  int64_t avail = (int64_t)n_in * 8;
+  // bits that really exist (n_in < 2^28), to tell padding zeros from data
+  int32_t avail = (int32_t)(n_in * 8u);
   uint32_t gpos = 0;                                              // bytes of the strip already in global memory
   uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);   // obuf index of byte gpos
   uint32_t q = 0;                                                 // bytes buffered
@@ -339,7 +345,7 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
     if (old < 0) {                         // first code after a clear is a literal
       if (code >= 256) { status = ST_CORRUPT; break; }
       if (shift + q + 1 > DEC_OBUF) flush(false);
-      if (w.lane == 0) obuf[shift + q] = (uint8_t)code;
+      obuf[shift + q] = (uint8_t)code;            // every lane stores the same byte
       q++;
       pos++;
       old = code;
@@ -367,10 +373,10 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
       while (i > 1) {
         const uint32_t e = tab[k];
         --i;
-        if (i < keep && w.lane == 0) dst[i] = (uint8_t)(e & 0xFFu);
+        if (i < keep) dst[i] = (uint8_t)(e & 0xFFu);
         k = (int)(e >> 20);
       }
-      if (w.lane == 0) dst[0] = (uint8_t)k;
+      dst[0] = (uint8_t)k;
     }
     q += keep;
     pos += keep;

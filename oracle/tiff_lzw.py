@@ -10,8 +10,15 @@ under /root/reference; this file restates its published LZW variant (TIFF 6.0 se
 libtiff's encoder policy: MSB-first codes, 9..12 bits, "early change", ClearCode at the start of
 every strip, table reset when code 4093 has been assigned, ratio check every 10000 input bytes)
 and Pillow's file layout (strips first, IFD after them, byte counts then offsets after the IFD).
-Pinned: tests/test_oracle_golden.py compares every byte of the files this module writes with
-the ones Pillow writes, and the pixels this module decodes with the ones Pillow decodes.
+Pinned: tests/test_tiff_host.py compares every byte of the files this module writes with the
+ones Pillow writes and with the files the reference's process_image_in_memory returned
+(tests/golden/tiff_lzw.npz), and the pixels this module decodes with the ones Pillow decodes.
+
+One byte is outside the contract: when the strips end on an odd offset libtiff seeks past one
+pad byte to word-align the IFD and never writes it; Pillow's in-memory sink leaves it as
+whatever its realloc'ed buffer held (observed 0x00 in one process and 0xd7 in another for the
+same image; MALLOC_PERTURB_ changes it).  This writer and the device writer store 0 there and
+same_file() ignores that byte.
 """
 import struct
 
@@ -22,6 +29,24 @@ CODE_CLEAR, CODE_EOI, CODE_FIRST = 256, 257, 258
 CODE_MAX = (1 << BITS_MAX) - 1
 CHECK_GAP = 10000
 STRIP_SIZE = 65536        # Pillow: rows per strip = min(STRIP_SIZE // stride, height), at least 1
+
+
+def same_file(a, b):
+    """True when two TIFF byte strings are identical up to the unwritten pad byte before the IFD."""
+    a, b = bytes(a), bytes(b)
+    if a == b:
+        return True
+    if len(a) != len(b) or len(b) < 8:
+        return False
+    try:
+        info = parse_tiff(b)
+    except (KeyError, ValueError, struct.error):
+        return False
+    end = max(o + c for o, c in zip(info["offsets"], info["counts"]))
+    ifd = struct.unpack(info["byteorder"] + "I", b[4:8])[0]
+    if end & 1 and ifd == end + 1:
+        return a[:end] == b[:end] and a[end + 1:] == b[end + 1:]
+    return False
 
 
 def rows_per_strip(width, height, bytes_per_pixel=2):

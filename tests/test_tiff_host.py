@@ -38,8 +38,29 @@ def images():
 @pytest.mark.parametrize("name,img", list(images()), ids=[n for n, _ in images()])
 def test_oracle_files_equal_pillow(name, img):
     ref = pil_lzw(img)
-    assert T.encode_tiff_lzw(img) == ref
+    assert T.same_file(T.encode_tiff_lzw(img), ref)
     np.testing.assert_array_equal(T.decode_tiff(ref), img)
+
+
+def test_same_file_ignores_only_the_pad_byte():
+    img = np.random.default_rng(3).integers(0, 65536, (40, 50)).astype(np.uint16)
+    for k in range(40):                                   # find an image whose strips end on an odd offset
+        img[0, 0] = k
+        f = bytearray(T.encode_tiff_lzw(img))
+        info = T.parse_tiff(bytes(f))
+        end = info["offsets"][-1] + info["counts"][-1]
+        if end & 1:
+            break
+    assert end & 1
+    g = bytearray(f)
+    g[end] = 0xD7
+    assert T.same_file(f, g) and T.same_file(g, f)
+    g[end - 1] ^= 1
+    assert not T.same_file(f, g)
+    g = bytearray(f)
+    g[end + 3] ^= 1
+    assert not T.same_file(f, g)
+    assert not T.same_file(f, f[:-1])
 
 
 def test_oracle_reads_predictor_and_uncompressed():
@@ -58,7 +79,7 @@ def test_oracle_reproduces_reference_files(golden_dir):
     for name in ("noise", "lzw_in", "flat", "tall", "ident"):
         src = T.decode_tiff(g[f"{name}_in"].tobytes())
         ow, oh = (int(v) for v in g[f"{name}_size"])
-        assert T.encode_tiff_lzw(o_lz.pil_resize(src, (oh, ow))) == g[f"{name}_file"].tobytes(), name
+        assert T.same_file(T.encode_tiff_lzw(o_lz.pil_resize(src, (oh, ow))), g[f"{name}_file"].tobytes()), name
 
 
 @pytest.fixture(scope="module")
