@@ -5,19 +5,19 @@
 // ips_tiff_lzw_encode_u16: uint16 planes in HBM -> complete little-endian TIFF files in HBM,
 // byte-identical to what Pillow 12.2 / libtiff 4.7 writes for the same pixels (strip LZW
 // streams, strip size, tag set and placement), so only compressed bytes cross PCIe.
-//   1. tiff_lzw_encode_kernel   one warp per strip, hash table in 32 KB of shared memory,
+//   1. tiff_lzw_encode_kernel   one warp per strip, hash table in 24 KB of shared memory,
 //                               strips land in fixed-capacity slots of the workspace;
 //   2. tiff_layout_kernel       one CTA per plane: scan of the strip sizes -> offsets, header,
 //                               IFD and the two strip arrays written behind the strips;
 //   3. tiff_gather_kernel       one CTA per strip: slot -> its place in the file.
 // ips_tiff_lzw_decode: LZW strips (anywhere in a device buffer) -> pixels; one warp per strip,
-// code table in 20 KB of shared memory, output staged through 8 KB of shared memory and
-// written in 16-byte vectors.  ips_tiff_fix_u16 undoes big-endian samples and horizontal
-// differencing (Predictor = 2).
+// 32 codes parsed per step (one per lane), a 15 KB table of output offsets per generation and
+// an 8 KB output window in shared memory, written out in 16-byte vectors (tiff_lzw_core.cuh).
+// ips_tiff_fix_u16 undoes big-endian samples and horizontal differencing (Predictor = 2).
 //
-// The codec is a serial state machine per strip: it is bound by shared-memory latency per
-// byte, not by HBM; parallelism is strips x planes (36 strips per 1080^2 plane, 180 per
-// 5-channel field), 6 resident encoder warps per SM.
+// The encoder is a serial state machine per strip, bound by the latency of one shared-memory
+// probe per byte, not by HBM; its parallelism is strips x planes (36 strips per 1080^2 plane,
+// 180 per 5-channel field), 9 resident warps per SM.
 #include "ips_common.cuh"
 #include "tiff_lzw_core.cuh"
 
@@ -171,12 +171,11 @@ tiff_lzw_decode_kernel(const uint8_t* __restrict__ src, const uint64_t* __restri
                        const uint32_t* __restrict__ src_bytes, uint8_t* __restrict__ dst,
                        const uint64_t* __restrict__ dst_off, const uint32_t* __restrict__ dst_bytes,
                        int32_t* __restrict__ status) {
-  __shared__ __align__(16) uint32_t tab[lz::DEC_CODES];
-  __shared__ __align__(16) uint8_t obuf[lz::DEC_OBUF];
-  __shared__ uint8_t firstc[lz::DEC_CODES];
+  __shared__ __align__(16) uint32_t otab[lz::PD_TAB];
+  __shared__ __align__(16) uint8_t win[lz::PD_WIN];
   const int s = blockIdx.x;
   lz::Warp w;
-  const int st = lz::decode_strip(src + src_off[s], src_bytes[s], dst + dst_off[s], dst_bytes[s], tab, firstc, obuf, w);
+  const int st = lz::decode_strip(src + src_off[s], src_bytes[s], dst + dst_off[s], dst_bytes[s], otab, win, w);
   if (w.lane == 0) status[s] = st;
 }
 

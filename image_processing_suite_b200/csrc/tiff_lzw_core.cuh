@@ -1,6 +1,7 @@
 // TIFF LZW strip coder, shared between the CUDA kernels of tiff.cu and the host harness of
-// tests/lzw_host_harness.cpp (which compiles this header with g++, a 1-lane "warp", to check
-// the state machines against Pillow/libtiff on the CPU-only authoring box).
+// tests/native/lzw_host_harness.cpp (which compiles this header with g++ -- the encoder with a
+// 1-lane "warp", the decoder with 32 threads standing in for the lanes -- to check the very
+// code the kernels run against Pillow/libtiff on the CPU-only authoring box).
 //
 // The stream format is TIFF 6.0 section 13 as libtiff writes it (the codec behind
 // img.save(..., compression='tiff_lzw'), Image_re-binning.py:19-21): MSB-first codes of 9..12
@@ -9,10 +10,11 @@
 // Following that policy to the letter makes the strips byte-identical to libtiff's, so the
 // files can be compared with cmp, not only decoded.
 //
-// Execution model: one warp per strip.  LZW is a serial state machine, so every lane runs the
-// same instruction stream on the same values (shared-memory reads broadcast, identical writes
-// collapse) and only lane 0 stores to global memory; the lanes split the work that does
-// parallelise -- clearing the 24 KB hash table and flushing decoded bytes in 16-byte vectors.
+// Execution model: one warp per strip.  Encoding is a serial state machine (the next match
+// starts where the previous one ended), so every lane runs the same instruction stream on the
+// same values (shared-memory reads broadcast, identical writes collapse), only lane 0 stores to
+// global memory and the lanes share the one job that parallelises, clearing the 24 KB hash
+// table.  Decoding is parallel across the lanes (see the decoder below).
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -28,7 +30,6 @@ namespace ips_lzw {
 enum : int { BITS_MIN = 9, BITS_MAX = 12, CODE_CLEAR = 256, CODE_EOI = 257, CODE_FIRST = 258, CODE_MAX = 4095 };
 enum : uint32_t { CHECK_GAP = 10000 };
 enum : uint32_t { ENC_SLOTS = 6144, ENC_EMPTY = 0xFFFFFFFFu };      // open addressing, load <= 0.63
-enum : uint32_t { DEC_CODES = 4096, DEC_OBUF = 4096 };
 enum : uint32_t { OVERFLOW = 0xFFFFFFFFu };
 enum : int { ST_OK = 0, ST_TRUNCATED = 1, ST_CORRUPT = 2, ST_OLD_STYLE = 3 };
 
@@ -38,7 +39,10 @@ struct Warp {
   __device__ __forceinline__ Warp() : lane(threadIdx.x & 31) {}
   static constexpr int n = 32;
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(0xffffffffu, v, (int)src); }
 };
+LZW_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__ffs((int)v) - 1u; }
 LZW_HD uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 LZW_HD uint32_t load_u32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 struct alignas(16) Vec16 { uint32_t a, b, c, d; };
@@ -51,6 +55,7 @@ struct Warp {
   static constexpr int n = 1;
   void sync() const {}
 };
+inline uint32_t ctz32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
 inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
 inline uint32_t load_u32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline void copy16(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, 16); }
@@ -240,158 +245,224 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
 // ------------------------------------------------------------------------------------------
 // decoder
 // ------------------------------------------------------------------------------------------
-// tab[k] = prefix << 20 | length << 8 | last byte, for k >= 258; firstc[k] = first byte of the string
-struct Decoder {
-  const uint8_t* in;
-  uint32_t n_in, ip;
-  uint64_t acc;      // top nb bits valid
-  int nb;
-  uint32_t nextw;    // next 32 input bits, loaded one refill ahead
+// A serial LZW decoder spends ~600 cycles per code on one warp.  This one parses 32 codes per
+// step, one per lane, using three facts about a table generation (the codes between two
+// ClearCodes):
+//   1. the width of the k-th code after a ClearCode depends on k alone (9 bits for k < 254,
+//      10 for k < 766, 11 for k < 1790, then 12), so every lane knows where its code starts;
+//   2. the string of code 258 + t is the string of the t-th code of the generation followed by
+//      the first byte of the (t+1)-th: those bytes are adjacent in the output, so the string is
+//      out[O_t .. O_t + L_t + 1), where O_t is the output offset of the t-th code.  One table
+//      of offsets per generation (O_t, 15 KB of shared memory) replaces the prefix/suffix
+//      dictionary; lengths are differences of neighbours;
+//   3. lengths depend on earlier lengths only (L_j = L_t + 1), offsets are their prefix sum:
+//      a few shuffle rounds and a warp scan per 32 codes.
+// Bytes go through an 8 KB circular window in shared memory (recent output, which is where
+// most references point) and leave for global memory in 16-byte vectors; references that fell
+// out of the window are read back from global memory.  Chunks whose strings are short are
+// copied one lane per code, in passes ordered by the in-chunk dependencies; chunks with long
+// strings are copied code by code with the lanes striding over the bytes.
+enum : uint32_t { PD_WIN = 8192, PD_TAB = 3840, PD_PAR_MAX = 512 };
 
-  LZW_HD uint32_t fetch_word() {      // 32 bits at ip (4-byte aligned address), zero-padded past the end
-    uint32_t v;
-    if (ip + 4 <= n_in) {
-      v = bswap32(load_u32(in + ip));
-    } else {
-      v = 0;
-      for (uint32_t k = 0; k < 4; ++k)
-        if (ip + k < n_in) v |= (uint32_t)in[ip + k] << (24 - 8 * k);
-    }
-    ip += 4;
+LZW_HD uint32_t code_bitpos(uint32_t k) {     // bit offset of the k-th code after a ClearCode
+  if (k <= 254u) return 9u * k;
+  if (k <= 766u) return 9u * 254u + 10u * (k - 254u);
+  if (k <= 1790u) return 9u * 254u + 10u * 512u + 11u * (k - 766u);
+  return 9u * 254u + 10u * 512u + 11u * 1024u + 12u * (k - 1790u);
+}
+LZW_HD int code_width(uint32_t k) { return k < 254u ? 9 : k < 766u ? 10 : k < 1790u ? 11 : 12; }
+
+struct BitReader {
+  const uint8_t* base;   // 4-byte aligned address at or before the first byte
+  uint32_t skew;         // bits between base and the first byte
+  uint32_t bytes;        // bytes from base to the end of the strip
+  LZW_HD void begin(const uint8_t* in, uint32_t n_in) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
+    base = in - a;
+    skew = 8u * a;
+    bytes = n_in + a;
+  }
+  LZW_HD uint32_t word(uint32_t idx) const {          // big-endian word idx, zero past the end
+    if (idx * 4u + 4u <= bytes) return bswap32(load_u32(base + idx * 4u));
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 4u; ++k)
+      if (idx * 4u + k < bytes) v |= (uint32_t)base[idx * 4u + k] << (24u - 8u * k);
     return v;
   }
-  LZW_HD void begin(const uint8_t* src, uint32_t n) {
-    in = src;
-    n_in = n;
-    ip = 0;
-    acc = 0;
-    nb = 0;
-    while (ip < n_in && ((reinterpret_cast<uintptr_t>(in + ip)) & 3u)) {
-      acc |= (uint64_t)in[ip++] << (56 - nb);
-      nb += 8;
-    }
-    nextw = fetch_word();
-  }
-  LZW_HD void refill() {
-    if (nb <= 32) {
-      acc |= (uint64_t)nextw << (32 - nb);
-      nb += 32;
-      nextw = fetch_word();
-    }
+  LZW_HD uint32_t code(uint32_t bitpos, int width) const {   // bitpos counted from the first byte
+    const uint32_t b = bitpos + skew;
+    const uint32_t hi = word(b >> 5), lo = word((b >> 5) + 1u);
+    const uint64_t both = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)((both << (b & 31u)) >> (64 - width));
   }
 };
 
-// Decodes one strip to out[0..n_out).  obuf: DEC_OBUF bytes of 16-byte aligned shared memory;
-// tab: DEC_CODES words; firstc: DEC_CODES bytes.  Returns a status; on any failure the
-// undecoded remainder is zero-filled so the output is deterministic.
+// Decodes one strip to out[0..n_out) with a full warp (W::n == 32).  otab: PD_TAB words, win:
+// PD_WIN bytes, 16-byte aligned.  n_in < 2^28.  Returns a status; on any failure the undecoded
+// remainder is zero-filled so the output is deterministic.
 template <class W>
-LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out, uint32_t* tab, uint8_t* firstc,
-                        uint8_t* obuf, const W& w) {
+LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out, uint32_t* otab, uint8_t* win,
+                        const W& w) {
+  const uint32_t lane = (uint32_t)w.lane;
   int status = ST_OK;
   if (n_in >= 2 && in[0] == 0 && (in[1] & 1)) status = ST_OLD_STYLE;   // pre-6.0 LSB-first streams
-  Decoder d;
-  d.begin(in, n_in);
-  // bits that really exist (n_in < 2^28), to tell padding zeros from data
-  int32_t avail = (int32_t)(n_in * 8u);
-  uint32_t gpos = 0;                                              // bytes of the strip already in global memory
-  uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);   // obuf index of byte gpos
-  uint32_t q = 0;                                                 // bytes buffered
-  uint32_t pos = 0;                                               // gpos + q
-  int nbits = BITS_MIN, free_ent = CODE_FIRST;
-  int old = -1, old_len = 0;
-  uint32_t old_first = 0;
+  BitReader br;
+  br.begin(in, n_in);
+  const uint32_t total_bits = n_in * 8u;
+  const uint32_t A = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);   // window index = (pos + A) mod PD_WIN
+  uint8_t* const gA = out - A;
+  uint32_t pos = 0;          // bytes decoded (all of them written to the window or beyond)
+  uint32_t flushed = 0;      // bytes [0, flushed) are in global memory
+  uint32_t gen_bit0 = 0;     // bit position of code 0 of the current generation
+  uint32_t kbase = 0;        // generation index of lane 0's code
 
-  auto flush = [&](bool final) {
+  // window bytes [flushed, frontier) -> global memory, whole 16-byte vectors unless final
+  auto flush = [&](uint32_t frontier, bool final) {
     w.sync();
-    uint8_t* g = out + gpos;                    // global address of obuf[shift]
-    const uint32_t n = q;
-    uint32_t head = (16u - shift) & 15u;
-    if (head > n) head = n;
-    uint32_t body = (n - head) & ~15u;
-    uint32_t tail = n - head - body;
-    for (uint32_t i = w.lane; i < head; i += W::n) g[i] = obuf[shift + i];
-    for (uint32_t i = w.lane * 16u; i < body; i += W::n * 16u) copy16(g + head + i, obuf + shift + head + i);
-    if (final) {
-      for (uint32_t i = w.lane; i < tail; i += W::n) g[head + body + i] = obuf[shift + head + body + i];
-      gpos += n;
-      q = 0;
-      shift = (shift + n) & 15u;
-    } else {
-      w.sync();
-      const uint32_t src = shift + head + body;       // a multiple of 16 whenever tail > 0
-      if (tail && w.lane == 0)
-        for (uint32_t i = 0; i < tail; ++i) obuf[i] = obuf[src + i];
-      gpos += head + body;
-      q = tail;
-      shift = tail ? 0u : ((shift + head + body) & 15u);
+    const uint32_t v0 = flushed + A;
+    uint32_t v1 = frontier + A;
+    if (!final) v1 &= ~15u;
+    if (v1 > v0) {
+      uint32_t head_end = (v0 + 15u) & ~15u;
+      if (head_end > v1) head_end = v1;
+      for (uint32_t v = v0 + lane; v < head_end; v += 32u) gA[v] = win[v & (PD_WIN - 1u)];
+      const uint32_t ve = v1 & ~15u;
+      for (uint32_t v = head_end + 16u * lane; v < ve; v += 512u) copy16(gA + v, win + (v & (PD_WIN - 1u)));
+      const uint32_t tail = ve > head_end ? ve : head_end;
+      for (uint32_t v = tail + lane; v < v1; v += 32u) gA[v] = win[v & (PD_WIN - 1u)];
+      flushed = v1 - A;
     }
     w.sync();
   };
 
   while (status == ST_OK && pos < n_out) {
-    d.refill();
-    if (avail < nbits) { status = ST_TRUNCATED; break; }
-    const int code = (int)(d.acc >> (64 - nbits));
-    d.acc <<= nbits;
-    d.nb -= nbits;
-    avail -= nbits;
-    if (code == CODE_EOI) { status = ST_TRUNCATED; break; }
-    if (code == CODE_CLEAR) {
-      free_ent = CODE_FIRST;
-      nbits = BITS_MIN;
-      old = -1;
-      continue;
+    // ---- this lane's code ----------------------------------------------------------------
+    const uint32_t k = kbase + lane;
+    const int width = code_width(k);
+    const uint32_t bp = gen_bit0 + code_bitpos(k);
+    const bool over = bp + (uint32_t)width > total_bits;
+    const uint32_t c = over ? (uint32_t)CODE_EOI : br.code(bp, width);
+    const uint32_t endmask = w.ballot(over || c == (uint32_t)CODE_CLEAR || c == (uint32_t)CODE_EOI);
+    uint32_t nvalid = endmask ? ctz32(endmask) : 32u;
+    const bool lit = c < 256u;
+    const int t = (int)c - CODE_FIRST;                     // generation index of the code that made this entry
+    const uint32_t badmask = w.ballot(lane < nvalid && !lit && t > (int)k - 1);
+    bool corrupt = false;
+    if (badmask && ctz32(badmask) < nvalid) {
+      nvalid = ctz32(badmask);
+      corrupt = true;
     }
-    if (old < 0) {                         // first code after a clear is a literal
-      if (code >= 256) { status = ST_CORRUPT; break; }
-      if (shift + q + 1 > DEC_OBUF) flush(false);
-      obuf[shift + q] = (uint8_t)code;            // every lane stores the same byte
-      q++;
-      pos++;
-      old = code;
-      old_len = 1;
-      old_first = (uint32_t)code;
-      continue;
+    const bool valid = lane < nvalid;
+    const uint32_t rel = (uint32_t)(t - (int)kbase) & 31u;   // source lane when the entry was made in this chunk
+    const bool far = t < (int)kbase;                         // entry made in an earlier chunk
+
+    // ---- string lengths: L = L_t + 1 --------------------------------------------------------
+    uint32_t len = (valid && lit) ? 1u : 0u;
+    bool have = !valid || lit;
+    if (valid && !lit && far) {
+      len = otab[t + 1] - otab[t] + 1u;
+      have = true;
     }
-    if (code > free_ent || (code == free_ent && free_ent >= (int)DEC_CODES)) { status = ST_CORRUPT; break; }
-    uint32_t first;
-    if (code < 256) first = (uint32_t)code;
-    else if (code == free_ent) first = old_first;
-    else first = firstc[code];
-    if (free_ent < (int)DEC_CODES) {       // entry = previous string + first byte of this one
-      tab[free_ent] = ((uint32_t)old << 20) | ((uint32_t)(old_len + 1) << 8) | first;
-      firstc[free_ent] = (uint8_t)old_first;
-    }
-    uint32_t len = code < 256 ? 1u : ((tab[code] >> 8) & 0xFFFu);
-    const uint32_t room = n_out - pos;
-    const uint32_t keep = len < room ? len : room;
-    if (shift + q + keep > DEC_OBUF) flush(false);
-    {
-      int k = code;
-      uint32_t i = len;
-      uint8_t* dst = obuf + shift + q;
-      while (i > 1) {
-        const uint32_t e = tab[k];
-        --i;
-        if (i < keep) dst[i] = (uint8_t)(e & 0xFFu);
-        k = (int)(e >> 20);
+    while (w.ballot(!have)) {
+      const uint32_t ls = w.shfl(len, rel);
+      const uint32_t hs = w.shfl(have ? 1u : 0u, rel);
+      if (!have && hs) {
+        len = ls + 1u;
+        have = true;
       }
-      dst[0] = (uint8_t)k;
     }
-    q += keep;
-    pos += keep;
-    old = code;
-    old_len = (int)len;
-    old_first = first;
-    if (free_ent < (int)DEC_CODES) {
-      free_ent++;
-      if (free_ent >= (1 << nbits) - 1 && nbits < BITS_MAX) nbits++;
+    // ---- output offsets: exclusive scan ---------------------------------------------------------
+    uint32_t incl = len;
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+      const uint32_t up = w.shfl(incl, (lane - d) & 31u);
+      if (lane >= d) incl += up;
+    }
+    const uint32_t total = w.shfl(incl, 31u);
+    const uint32_t off = pos + incl - len;                    // O_k
+    if (valid && k < PD_TAB) otab[k] = off;
+    if (lane == 0 && kbase + nvalid < PD_TAB) otab[kbase + nvalid] = pos + total;
+    const uint32_t room = n_out - pos;
+    const uint32_t chunk = total < room ? total : room;       // bytes this chunk writes
+    uint32_t cp = 0;                                          // bytes this lane's code writes
+    if (valid && off < n_out) cp = len < n_out - off ? len : n_out - off;
+    w.sync();
+    // source offset O_t of the string this code copies
+    const uint32_t src_far = (valid && !lit && far) ? otab[t] : 0u;
+    const uint32_t src_near = w.shfl(off, rel);
+    const uint32_t src = far ? src_far : src_near;
+
+    // ---- copy -----------------------------------------------------------------------------------
+    if (chunk <= PD_PAR_MAX) {
+      const uint32_t wr_end = pos + chunk;
+      if (wr_end - flushed > PD_WIN - 16u) flush(pos, false);
+      bool done = cp == 0u;
+      if (!done && lit) {
+        win[(off + A) & (PD_WIN - 1u)] = (uint8_t)c;
+        done = true;
+      }
+      for (;;) {
+        w.sync();
+        const uint32_t dm = w.ballot(done);
+        if (dm == 0xFFFFFFFFu) break;
+        if (!done) {
+          const bool dep1 = far || ((dm >> rel) & 1u);
+          const uint32_t u = (uint32_t)t + 1u;                // the code that supplies the last byte
+          const bool dep2 = u == k || u < kbase || ((dm >> ((u - kbase) & 31u)) & 1u);
+          if (dep1 && dep2) {
+            const uint32_t period = off - src;
+            for (uint32_t i = 0; i < cp; ++i) {
+              uint32_t sp = src + i;
+              if (sp >= off) sp -= period;                    // the entry being defined right now (KwKwK)
+              const uint8_t b = sp + PD_WIN > wr_end ? win[(sp + A) & (PD_WIN - 1u)] : out[sp];
+              win[(off + i + A) & (PD_WIN - 1u)] = b;
+            }
+            done = true;
+          }
+        }
+      }
+    } else {
+      for (uint32_t q = 0; q < nvalid; ++q) {
+        const uint32_t cq = w.shfl(c, q), oq = w.shfl(off, q), nq = w.shfl(cp, q), sq = w.shfl(src, q);
+        if (nq == 0u) break;
+        const uint32_t wr_end = oq + nq;
+        if (wr_end - flushed > PD_WIN - 16u) flush(oq, false);
+        if (cq < 256u) {
+          if (lane == 0) win[(oq + A) & (PD_WIN - 1u)] = (uint8_t)cq;
+        } else {
+          const uint32_t period = oq - sq;
+          for (uint32_t i = lane; i < nq; i += 32u) {
+            uint32_t sp = sq + i;
+            if (sp >= oq) sp -= period;
+            const uint8_t b = sp + PD_WIN > wr_end ? win[(sp + A) & (PD_WIN - 1u)] : out[sp];
+            win[(oq + i + A) & (PD_WIN - 1u)] = b;
+          }
+        }
+        w.sync();
+      }
+    }
+    pos += chunk;
+    if (pos >= n_out) break;
+    if (corrupt) {
+      status = ST_CORRUPT;
+      break;
+    }
+    if (nvalid < 32u) {                                       // a terminator sits in lane nvalid
+      const uint32_t ce = w.shfl(c, nvalid);
+      const uint32_t oe = w.shfl(over ? 1u : 0u, nvalid);
+      if (oe || ce == (uint32_t)CODE_EOI) {
+        status = ST_TRUNCATED;
+        break;
+      }
+      gen_bit0 = w.shfl(bp, nvalid) + (uint32_t)w.shfl((uint32_t)width, nvalid);
+      kbase = 0;
+    } else {
+      kbase += 32u;
     }
   }
-  flush(true);
+  flush(pos, true);
   if (pos < n_out) {
     if (status == ST_OK) status = ST_TRUNCATED;
-    for (uint32_t i = pos + w.lane; i < n_out; i += W::n) out[i] = 0;
+    for (uint32_t i = pos + lane; i < n_out; i += 32u) out[i] = 0;
   }
   return status;
 }

@@ -1,9 +1,42 @@
-// Host build of the LZW strip coder of image_processing_suite_b200/csrc/tiff_lzw_core.cuh with a
-// 1-lane "warp": lets the CPU-only suite check the exact state machines the CUDA kernels run
-// against Pillow/libtiff.  Test infrastructure only; libips.so does not contain this code path.
+// Host build of the LZW strip coder of image_processing_suite_b200/csrc/tiff_lzw_core.cuh: the
+// encoder with a 1-lane "warp", the decoder with 32 threads standing in for the 32 lanes
+// (ballot / shuffle / syncwarp through a barrier).  Lets the CPU-only suite check the code the
+// CUDA kernels run against Pillow/libtiff.  Test infrastructure only; libips.so does not
+// contain this code path.
 #include <stdint.h>
 #include <stdlib.h>
+#include <barrier>
+#include <thread>
+#include <vector>
 #include "../../image_processing_suite_b200/csrc/tiff_lzw_core.cuh"
+
+namespace {
+struct Shared {
+  std::barrier<> bar{32};
+  uint32_t slot[32];
+};
+struct Warp32 {
+  int lane;
+  Shared* sh;
+  static constexpr int n = 32;
+  void sync() const { sh->bar.arrive_and_wait(); }
+  uint32_t shfl(uint32_t v, uint32_t src) const {
+    sh->slot[lane] = v;
+    sh->bar.arrive_and_wait();
+    const uint32_t r = sh->slot[src & 31u];
+    sh->bar.arrive_and_wait();
+    return r;
+  }
+  uint32_t ballot(bool p) const {
+    sh->slot[lane] = p ? 1u : 0u;
+    sh->bar.arrive_and_wait();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= sh->slot[i] << i;
+    sh->bar.arrive_and_wait();
+    return r;
+  }
+};
+}  // namespace
 
 extern "C" {
 uint64_t harness_bound(uint64_t n) { return ips_lzw::encode_bound(n); }
@@ -15,12 +48,20 @@ uint32_t harness_encode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t ca
   return r;
 }
 int harness_decode(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out) {
-  uint32_t* tab = (uint32_t*)aligned_alloc(16, ips_lzw::DEC_CODES * 4);
-  uint8_t* firstc = (uint8_t*)malloc(ips_lzw::DEC_CODES);
-  uint8_t* obuf = (uint8_t*)aligned_alloc(16, ips_lzw::DEC_OBUF);
-  ips_lzw::Warp w;
-  const int st = ips_lzw::decode_strip(in, n_in, out, n_out, tab, firstc, obuf, w);
-  free(tab); free(firstc); free(obuf);
-  return st;
+  uint32_t* otab = (uint32_t*)aligned_alloc(16, ips_lzw::PD_TAB * 4);
+  uint8_t* win = (uint8_t*)aligned_alloc(16, ips_lzw::PD_WIN);
+  Shared sh;
+  int status[32];
+  std::vector<std::thread> lanes;
+  for (int l = 0; l < 32; ++l)
+    lanes.emplace_back([&, l] {
+      Warp32 w{l, &sh};
+      status[l] = ips_lzw::decode_strip(in, n_in, out, n_out, otab, win, w);
+    });
+  for (auto& t : lanes) t.join();
+  for (int l = 1; l < 32; ++l)
+    if (status[l] != status[0]) return -100 - l;   // the lanes must agree
+  free(otab); free(win);
+  return status[0];
 }
 }

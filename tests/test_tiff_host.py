@@ -85,7 +85,7 @@ def test_oracle_reproduces_reference_files(golden_dir):
 @pytest.fixture(scope="module")
 def harness(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("lzw") / "lzw_harness.so")
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", os.path.join(ROOT, "tests", "native", "lzw_host_harness.cpp"), "-o", so],
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", os.path.join(ROOT, "tests", "native", "lzw_host_harness.cpp"), "-o", so],
                    check=True)
     h = ctypes.CDLL(so)
     h.harness_bound.restype = ctypes.c_uint64
