@@ -5,7 +5,7 @@
 // ips_tiff_lzw_encode_u16: uint16 planes in HBM -> complete little-endian TIFF files in HBM,
 // byte-identical to what Pillow 12.2 / libtiff 4.7 writes for the same pixels (strip LZW
 // streams, strip size, tag set and placement), so only compressed bytes cross PCIe.
-//   1. tiff_lzw_encode_kernel   one warp per strip, hash table in 24 KB of shared memory,
+//   1. tiff_lzw_encode_kernel   one warp per strip, hash table in 21.5 KB of shared memory,
 //                               strips land in fixed-capacity slots of the workspace;
 //   2. tiff_layout_kernel       one CTA per plane: scan of the strip sizes -> offsets, header,
 //                               IFD and the two strip arrays written behind the strips;
@@ -17,7 +17,7 @@
 //
 // The encoder is a serial state machine per strip, bound by the latency of one shared-memory
 // probe per byte, not by HBM; its parallelism is strips x planes (36 strips per 1080^2 plane,
-// 180 per 5-channel field), 9 resident warps per SM.
+// 180 per 5-channel field), 10 resident warps per SM.
 #include "ips_common.cuh"
 #include "tiff_lzw_core.cuh"
 

@@ -13,7 +13,7 @@
 // Execution model: one warp per strip.  Encoding is a serial state machine (the next match
 // starts where the previous one ended), so every lane runs the same instruction stream on the
 // same values (shared-memory reads broadcast, identical writes collapse), only lane 0 stores to
-// global memory and the lanes share the one job that parallelises, clearing the 24 KB hash
+// global memory and the lanes share the one job that parallelises, clearing the 21.5 KB hash
 // table.  Decoding is parallel across the lanes (see the decoder below).
 #pragma once
 #include <stdint.h>
@@ -29,7 +29,7 @@ namespace ips_lzw {
 
 enum : int { BITS_MIN = 9, BITS_MAX = 12, CODE_CLEAR = 256, CODE_EOI = 257, CODE_FIRST = 258, CODE_MAX = 4095 };
 enum : uint32_t { CHECK_GAP = 10000 };
-enum : uint32_t { ENC_SLOTS = 6144, ENC_EMPTY = 0xFFFFFFFFu };      // open addressing, load <= 0.63
+enum : uint32_t { ENC_SLOTS = 5504, ENC_EMPTY = 0xFFFFFFFFu };      // open addressing, load <= 0.70; 21.5 KB: 10 strips per SM
 enum : uint32_t { OVERFLOW = 0xFFFFFFFFu };
 enum : int { ST_OK = 0, ST_TRUNCATED = 1, ST_CORRUPT = 2, ST_OLD_STYLE = 3 };
 
@@ -232,13 +232,24 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
   if (n == 0) return e.finish(false);
   e.put(CODE_CLEAR);
   e.ent = in[0];
-  uint32_t next = n > 1 ? in[1] : 0u;          // one byte of look-ahead keeps the load off the chain
-#pragma unroll 1
-  for (uint32_t i = 1; i < n; ++i) {
-    const uint32_t c = next;
-    if (i + 1 < n) next = in[i + 1];
-    e.byte(c, i + 1, w);
+  uint32_t i = 1;
+  while (i < n && (reinterpret_cast<uintptr_t>(in + i) & 3u)) {      // up to the first aligned word
+    e.byte(in[i], i + 1, w);
+    ++i;
   }
+  if (i + 4u <= n) {
+    uint32_t next = load_u32(in + i);            // one word of look-ahead keeps the load off the chain
+#pragma unroll 1
+    for (; i + 4u <= n; i += 4u) {
+      const uint32_t cur = next;
+      if (i + 8u <= n) next = load_u32(in + i + 4u);
+      e.byte(cur & 0xFFu, i + 1, w);
+      e.byte((cur >> 8) & 0xFFu, i + 2, w);
+      e.byte((cur >> 16) & 0xFFu, i + 3, w);
+      e.byte(cur >> 24, i + 4, w);
+    }
+  }
+  for (; i < n; ++i) e.byte(in[i], i + 1, w);
   return e.finish(true);
 }
 
