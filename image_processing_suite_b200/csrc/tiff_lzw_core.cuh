@@ -300,11 +300,16 @@ struct BitReader {
       if (idx * 4u + k < bytes) v |= (uint32_t)base[idx * 4u + k] << (24u - 8u * k);
     return v;
   }
-  LZW_HD uint32_t code(uint32_t bitpos, int width) const {   // bitpos counted from the first byte
-    const uint32_t b = bitpos + skew;
-    const uint32_t hi = word(b >> 5), lo = word((b >> 5) + 1u);
+  // the two words that hold the code at bitpos (counted from the first byte) ...
+  LZW_HD void fetch(uint32_t bitpos, uint32_t& hi, uint32_t& lo) const {
+    const uint32_t idx = (bitpos + skew) >> 5;
+    hi = word(idx);
+    lo = word(idx + 1u);
+  }
+  // ... and the code itself
+  LZW_HD uint32_t code(uint32_t bitpos, int width, uint32_t hi, uint32_t lo) const {
     const uint64_t both = ((uint64_t)hi << 32) | lo;
-    return (uint32_t)((both << (b & 31u)) >> (64 - width));
+    return (uint32_t)((both << ((bitpos + skew) & 31u)) >> (64 - width));
   }
 };
 
@@ -326,6 +331,7 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
   uint32_t flushed = 0;      // bytes [0, flushed) are in global memory
   uint32_t gen_bit0 = 0;     // bit position of code 0 of the current generation
   uint32_t kbase = 0;        // generation index of lane 0's code
+  uint32_t pre_hi = 0, pre_lo = 0, pre_bit0 = 0xFFFFFFFFu, pre_kbase = 0;   // prefetched input words
 
   // window bytes [flushed, frontier) -> global memory, whole 16-byte vectors unless final
   auto flush = [&](uint32_t frontier, bool final) {
@@ -352,7 +358,14 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
     const int width = code_width(k);
     const uint32_t bp = gen_bit0 + code_bitpos(k);
     const bool over = bp + (uint32_t)width > total_bits;
-    const uint32_t c = over ? (uint32_t)CODE_EOI : br.code(bp, width);
+    uint32_t hi = pre_hi, lo = pre_lo;
+    if (pre_bit0 != gen_bit0 || pre_kbase != kbase) br.fetch(bp, hi, lo);   // a ClearCode moved the generation
+    const uint32_t c = over ? (uint32_t)CODE_EOI : br.code(bp, width, hi, lo);
+    // the words of this lane's code in the next chunk, assuming no ClearCode in this one: in flight
+    // while the lengths, offsets and copies below run
+    pre_bit0 = gen_bit0;
+    pre_kbase = kbase + 32u;
+    br.fetch(gen_bit0 + code_bitpos(k + 32u), pre_hi, pre_lo);
     const uint32_t endmask = w.ballot(over || c == (uint32_t)CODE_CLEAR || c == (uint32_t)CODE_EOI);
     uint32_t nvalid = endmask ? ctz32(endmask) : 32u;
     const bool lit = c < 256u;

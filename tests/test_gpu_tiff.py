@@ -199,3 +199,34 @@ def test_rebinning_batch_and_host_decoded_inputs():
     assert Image_rebinning.process_image_in_memory(buf.getvalue(), (80, 60)) == outs[0]
     with pytest.raises(Exception):
         Image_rebinning.process_image_in_memory(b"not an image")
+
+
+@pytest.mark.parametrize("shape", [(24, 97, 131), (12, 331, 1000)])
+def test_codec_fuzz_against_pillow(shape):
+    """Planes of different statistics in one launch: files equal Pillow's, pixels come back."""
+    require_gpu()
+    from image_processing_suite_b200.scripts import tiffio
+    rng = np.random.default_rng(31)
+    P, H, W = shape
+    a = np.empty(shape, np.uint16)
+    for p in range(P):
+        kind = p % 6
+        if kind == 0:
+            a[p] = rng.integers(0, rng.integers(1, 4), (H, W))
+        elif kind == 1:
+            a[p] = np.clip(rng.normal(rng.integers(100, 3000), rng.integers(1, 200), (H, W)), 0, 65535)
+        elif kind == 2:
+            a[p] = np.repeat(rng.integers(0, 65536, (H, (W + 7) // 8)), 8, axis=1)[:, :W]
+        elif kind == 3:
+            a[p] = np.tile(rng.integers(0, 4096, rng.integers(2, 300)), H * W)[:H * W].reshape(H, W)
+        elif kind == 4:
+            a[p] = rng.integers(0, 65536, (H, W))
+        else:
+            a[p] = (np.add.outer(np.arange(H), np.arange(W)) // 3) % 65536
+    files = tiffio.encode_lzw_from_device(dev(a))
+    refs = [pil_file(a[p], compression="tiff_lzw") for p in range(P)]
+    for p in range(P):
+        assert T.same_file(files[p], refs[p]), p
+    np.testing.assert_array_equal(host(tiffio.decode_to_device(refs)), a)
+    pred = [pil_file(a[p], compression="tiff_lzw", tiffinfo={317: 2}) for p in range(P)]
+    np.testing.assert_array_equal(host(tiffio.decode_to_device(pred)), a)

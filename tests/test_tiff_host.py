@@ -176,3 +176,37 @@ def test_product_parser_matches_oracle_and_rejects_other_layouts():
         tiffio.parse(buf.getvalue())
     with pytest.raises(tiffio.Unsupported):
         tiffio.parse(b"II*\x00\xff\xff\xff\x7f")
+
+
+def _fuzz_strip(rng, kind, n):
+    if kind == 0:      # few symbols: long strings, references far beyond the decoder's output window
+        return rng.integers(0, rng.integers(1, 4), n, dtype=np.uint8)
+    if kind == 1:      # 16-bit samples with a quiet high byte, like a camera image
+        return np.clip(rng.normal(rng.integers(100, 3000), rng.integers(1, 200), n // 2), 0, 65535).astype("<u2").view(np.uint8)
+    if kind == 2:      # runs of random length
+        out = np.repeat(rng.integers(0, 256, n // 4 + 1, dtype=np.uint8), rng.integers(1, 40, n // 4 + 1))
+        return out[:n]
+    if kind == 3:      # periodic with noise
+        base = np.tile(rng.integers(0, 256, rng.integers(2, 700), dtype=np.uint8), n)[:n].copy()
+        flip = rng.random(n) < 0.01
+        base[flip] = rng.integers(0, 256, int(flip.sum()), dtype=np.uint8)
+        return base
+    return rng.integers(0, 256, n, dtype=np.uint8)   # incompressible
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_kernel_state_machines_fuzz(harness, seed):
+    """Random strips of five entropy classes and odd lengths: the kernels' encoder equals the
+    oracle's libtiff restatement, the kernels' decoder returns the bytes, truncated requests too."""
+    rng = np.random.default_rng(1000 + seed)
+    kind = seed % 5
+    n = int(rng.integers(1, 70000))
+    raw = np.ascontiguousarray(_fuzz_strip(rng, kind, n)).tobytes()
+    off = int(rng.integers(0, 4))
+    comp = _enc(harness, raw, off)
+    assert comp == T.lzw_encode_strip(raw)
+    st, px = _dec(harness, comp, len(raw), int(rng.integers(0, 4)), int(rng.integers(0, 16)))
+    assert st == 0 and px == raw
+    cut = int(rng.integers(1, len(raw) + 1))
+    st, px = _dec(harness, comp, cut, 0, int(rng.integers(0, 16)))
+    assert st == 0 and px == raw[:cut]
