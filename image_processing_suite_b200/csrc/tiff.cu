@@ -11,7 +11,7 @@
 //                               IFD and the two strip arrays written behind the strips;
 //   3. tiff_gather_kernel       one CTA per strip: slot -> its place in the file.
 // ips_tiff_lzw_decode: LZW strips (anywhere in a device buffer) -> pixels; one warp per strip,
-// 32 codes parsed per step (one per lane), a 15 KB table of output offsets per generation and
+// 32 codes parsed per step (one per lane), an 8.4 KB table of output offsets per generation and
 // an 8 KB output window in shared memory, written out in 16-byte vectors (tiff_lzw_core.cuh).
 // ips_tiff_fix_u16 undoes big-endian samples and horizontal differencing (Predictor = 2).
 //
@@ -171,11 +171,12 @@ tiff_lzw_decode_kernel(const uint8_t* __restrict__ src, const uint64_t* __restri
                        const uint32_t* __restrict__ src_bytes, uint8_t* __restrict__ dst,
                        const uint64_t* __restrict__ dst_off, const uint32_t* __restrict__ dst_bytes,
                        int32_t* __restrict__ status) {
-  __shared__ __align__(16) uint32_t otab[lz::PD_TAB];
+  __shared__ __align__(16) uint16_t orel[lz::PD_TAB];
+  __shared__ uint32_t obase[lz::PD_TAB / 16];
   __shared__ __align__(16) uint8_t win[lz::PD_WIN];
   const int s = blockIdx.x;
   lz::Warp w;
-  const int st = lz::decode_strip(src + src_off[s], src_bytes[s], dst + dst_off[s], dst_bytes[s], otab, win, w);
+  const int st = lz::decode_strip(src + src_off[s], src_bytes[s], dst + dst_off[s], dst_bytes[s], orel, obase, win, w);
   if (w.lane == 0) status[s] = st;
 }
 

@@ -264,8 +264,8 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
 //   2. the string of code 258 + t is the string of the t-th code of the generation followed by
 //      the first byte of the (t+1)-th: those bytes are adjacent in the output, so the string is
 //      out[O_t .. O_t + L_t + 1), where O_t is the output offset of the t-th code.  One table
-//      of offsets per generation (O_t, 15 KB of shared memory) replaces the prefix/suffix
-//      dictionary; lengths are differences of neighbours;
+//      of offsets per generation (O_t; 8.4 KB of shared memory as 16-bit offsets within groups
+//      of 16 codes) replaces the prefix/suffix dictionary; lengths are differences of neighbours;
 //   3. lengths depend on earlier lengths only (L_j = L_t + 1), offsets are their prefix sum:
 //      a few shuffle rounds and a warp scan per 32 codes.
 // Bytes go through an 8 KB circular window in shared memory (recent output, which is where
@@ -313,11 +313,11 @@ struct BitReader {
   }
 };
 
-// Decodes one strip to out[0..n_out) with a full warp (W::n == 32).  otab: PD_TAB words, win:
+// Decodes one strip to out[0..n_out) with a full warp (W::n == 32).  orel: PD_TAB halfwords, obase: PD_TAB / 16 words, win:
 // PD_WIN bytes, 16-byte aligned.  n_in < 2^28.  Returns a status; on any failure the undecoded
 // remainder is zero-filled so the output is deterministic.
 template <class W>
-LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out, uint32_t* otab, uint8_t* win,
+LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out, uint16_t* orel, uint32_t* obase, uint8_t* win,
                         const W& w) {
   const uint32_t lane = (uint32_t)w.lane;
   int status = ST_OK;
@@ -384,7 +384,7 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
     uint32_t len = (valid && lit) ? 1u : 0u;
     bool have = !valid || lit;
     if (valid && !lit && far) {
-      len = otab[t + 1] - otab[t] + 1u;
+      len = (obase[(t + 1) >> 4] + orel[t + 1]) - (obase[t >> 4] + orel[t]) + 1u;
       have = true;
     }
     while (w.ballot(!have)) {
@@ -403,15 +403,23 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
     }
     const uint32_t total = w.shfl(incl, 31u);
     const uint32_t off = pos + incl - len;                    // O_k
-    if (valid && k < PD_TAB) otab[k] = off;
-    if (lane == 0 && kbase + nvalid < PD_TAB) otab[kbase + nvalid] = pos + total;
+    // O_k = obase[k / 16] + orel[k]: 16 consecutive strings span at most 16 * 3839 bytes
+    const uint32_t group0 = w.shfl(off, lane & 16u);
+    if (valid && k < PD_TAB) {
+      orel[k] = (uint16_t)(off - group0);
+      if ((lane & 15u) == 0u) obase[k >> 4] = off;
+    }
+    if (lane == 0 && nvalid == 32u && kbase + 32u < PD_TAB) {   // the next chunk's first offset closes this one's last length
+      orel[kbase + 32u] = 0;
+      obase[(kbase + 32u) >> 4] = pos + total;
+    }
     const uint32_t room = n_out - pos;
     const uint32_t chunk = total < room ? total : room;       // bytes this chunk writes
     uint32_t cp = 0;                                          // bytes this lane's code writes
     if (valid && off < n_out) cp = len < n_out - off ? len : n_out - off;
     w.sync();
     // source offset O_t of the string this code copies
-    const uint32_t src_far = (valid && !lit && far) ? otab[t] : 0u;
+    const uint32_t src_far = (valid && !lit && far) ? obase[t >> 4] + orel[t] : 0u;
     const uint32_t src_near = w.shfl(off, rel);
     const uint32_t src = far ? src_far : src_near;
 

@@ -48,7 +48,8 @@ uint32_t harness_encode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t ca
   return r;
 }
 int harness_decode(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out) {
-  uint32_t* otab = (uint32_t*)aligned_alloc(16, ips_lzw::PD_TAB * 4);
+  uint16_t* orel = (uint16_t*)aligned_alloc(16, ips_lzw::PD_TAB * 2);
+  uint32_t* obase = (uint32_t*)aligned_alloc(16, ips_lzw::PD_TAB / 16 * 4);
   uint8_t* win = (uint8_t*)aligned_alloc(16, ips_lzw::PD_WIN);
   Shared sh;
   int status[32];
@@ -56,12 +57,12 @@ int harness_decode(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_ou
   for (int l = 0; l < 32; ++l)
     lanes.emplace_back([&, l] {
       Warp32 w{l, &sh};
-      status[l] = ips_lzw::decode_strip(in, n_in, out, n_out, otab, win, w);
+      status[l] = ips_lzw::decode_strip(in, n_in, out, n_out, orel, obase, win, w);
     });
   for (auto& t : lanes) t.join();
   for (int l = 1; l < 32; ++l)
     if (status[l] != status[0]) return -100 - l;   // the lanes must agree
-  free(otab); free(win);
+  free(orel); free(obase); free(win);
   return status[0];
 }
 }
