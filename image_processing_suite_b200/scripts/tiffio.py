@@ -123,7 +123,7 @@ def decode_to_device(files, device=None):
     for f in files:
         base.append(total)
         total += (len(f) + 15) // 16 * 16
-    host = torch.empty((total,), dtype=torch.uint8).pin_memory() if total else torch.empty((0,), dtype=torch.uint8)
+    host = torch.empty((total,), dtype=torch.uint8, pin_memory=True)      # staging block from torch's pinned-memory cache
     hv = host.numpy()
     for b, f in zip(base, files):
         hv[b:b + len(f)] = np.frombuffer(f, dtype=np.uint8)
