@@ -110,7 +110,7 @@ def _corrected_and_pct(img_u16, illum):
     function is float32-exact the fused kernel computes the divide-side PercentMaximal."""
     import torch
     from .. import ops
-    raw = torch.from_numpy(np.ascontiguousarray(img_u16)).cuda()
+    raw = img_u16 if isinstance(img_u16, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img_u16)).cuda()
     if illum is None or img_u16.shape != illum.shape:        # silently uncorrected (:148-153)
         r = ops.preprocess_fused(raw[None, None, None], None, bin=1, want_maxproj=False, want_binned=False,
                                  want_pct_maximal=True)
@@ -138,9 +138,14 @@ def process_site(site_data):
                 if not os.path.exists(path):
                     site_results[f"QC_Error_{ch_name}"] = "File Not Found"
                     continue
-                img = tiffio.read(path)
+                with open(path, "rb") as fh:
+                    data = fh.read()
+                try:
+                    img = tiffio.decode_to_device([data])[0]         # strips decoded on the GPU (K7)
+                except tiffio.Unsupported:
+                    img = tiffio.decode(data)
                 illum = illum_cache[i] if illum_cache and illum_cache[i] is not None else None
-                if img.dtype == np.uint16 and img.ndim == 2:
+                if isinstance(img, torch.Tensor) or (img.dtype == np.uint16 and img.ndim == 2):
                     corrected, pct = _corrected_and_pct(img, illum)
                     try:
                         radii, _, powersum = rps(corrected)

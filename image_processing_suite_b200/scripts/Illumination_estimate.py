@@ -41,7 +41,8 @@ def estimate(load_data, data_path, channels, filter_size=200.0, robust_frac=0.02
         nonlocal est
         if not buf:
             return
-        dev = torch.from_numpy(np.stack(buf)).cuda()          # [F][C][H][W]
+        flat = tiffio.load_planes([b for site in buf for b in site])      # TIFF strips decoded on the GPU (K7)
+        dev = flat.reshape(len(buf), len(cols), flat.shape[1], flat.shape[2])   # [F][C][H][W]
         if mode == 'mean':
             if est is None:
                 est = ops.IllumEstimator(dev.shape[1], dev.shape[2], dev.shape[3])
@@ -51,8 +52,11 @@ def estimate(load_data, data_path, channels, filter_size=200.0, robust_frac=0.02
         buf.clear()
 
     for _, row in df.iterrows():
-        planes = [tiffio.read(os.path.join(data_path, row[c])) for c in cols]
-        buf.append(np.stack(planes))
+        site = []
+        for c in cols:
+            with open(os.path.join(data_path, row[c]), "rb") as fh:
+                site.append(fh.read())
+        buf.append(site)
         if len(buf) == batch:
             flush()
     flush()
