@@ -29,13 +29,14 @@ __global__ void __launch_bounds__(32)
 tiff_lzw_encode_kernel(const uint8_t* __restrict__ planes, uint8_t* __restrict__ slots, uint32_t* __restrict__ strip_bytes,
                        size_t plane_bytes, uint32_t row_bytes, int H, int rps, int S, uint32_t cap) {
   __shared__ __align__(16) uint32_t table[lz::ENC_SLOTS];
+  __shared__ uint32_t stage[lz::PE_STAGE];
   const int s = blockIdx.x, p = blockIdx.y;
   const int r0 = s * rps;
   const int rows = min(rps, H - r0);
   const uint8_t* in = planes + (size_t)p * plane_bytes + (size_t)r0 * row_bytes;
   const size_t slot = (size_t)p * S + s;
   lz::Warp w;
-  const uint32_t n = lz::encode_strip(in, (uint32_t)rows * row_bytes, slots + slot * cap, cap, table, w);
+  const uint32_t n = lz::encode_strip_par(in, (uint32_t)rows * row_bytes, slots + slot * cap, cap, table, stage, w);
   if (w.lane == 0) strip_bytes[slot] = n;
 }
 

@@ -41,8 +41,13 @@ struct Warp {
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
   __device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(0xffffffffu, v, (int)src); }
+  __device__ __forceinline__ uint32_t reduce_or(uint32_t v) const { return __reduce_or_sync(0xffffffffu, v); }
+  __device__ __forceinline__ uint32_t match_any(uint32_t v) const { return __match_any_sync(0xffffffffu, v); }
+  __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
+  __device__ __forceinline__ uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) const { return atomicCAS(p, cmp, v); }
 };
 LZW_HD uint32_t ctz32(uint32_t v) { return (uint32_t)__ffs((int)v) - 1u; }
+LZW_HD uint32_t popc32(uint32_t v) { return (uint32_t)__popc(v); }
 LZW_HD uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 LZW_HD uint32_t load_u32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 struct alignas(16) Vec16 { uint32_t a, b, c, d; };
@@ -56,6 +61,7 @@ struct Warp {
   void sync() const {}
 };
 inline uint32_t ctz32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
+inline uint32_t popc32(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
 inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
 inline uint32_t load_u32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline void copy16(uint8_t* dst, const uint8_t* src) { memcpy(dst, src, 16); }
@@ -251,6 +257,241 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
   }
   for (; i < n; ++i) e.byte(in[i], i + 1, w);
   return e.finish(true);
+}
+
+// ------------------------------------------------------------------------------------------
+// lane-parallel encoder
+// ------------------------------------------------------------------------------------------
+// Greedy LZW parsing is serial only through the phrase boundaries.  Each lane therefore walks the
+// dictionary from its own byte of a 32-byte window as if a phrase started there; the boundaries
+// are then found by pointer doubling over "start + length" (five shuffle rounds), and every lane
+// that really starts a phrase emits its code (bit offsets by a warp scan, atomicOr into a staging
+// word buffer) and inserts its new entry (atomicCAS along the probe path) at once.  The walks
+// see the dictionary as of the window start; the only way an entry made inside the window can
+// change a later phrase is by extending it at its failing (node, byte) pair, i.e. when two
+// phrases of the window fail on the same pair -- the window is cut before the second one and
+// the next window starts there.  Windows are also cut right after a phrase at which libtiff
+// resets the table or evaluates the compression ratio, so those decisions are taken by uniform
+// scalar code between windows with exactly libtiff's counters.
+enum : uint32_t { PE_STAGE = 16 };   // staging words: 31 carried bits + 32 codes x 12 bits < 16 words
+
+template <class W>
+struct ParEncoder {
+  const W& w;
+  uint32_t lane;
+  uint32_t* tab;
+  uint32_t* stage;
+  uint8_t* out;
+  uint32_t cap, op, carry, obits;
+  bool overflow;
+
+  LZW_HD ParEncoder(const W& w_) : w(w_) {}
+
+  // every lane contributes `wd` bits of `code` (wd == 0: nothing), in lane order
+  LZW_HD void emit(uint32_t code, uint32_t wd) {
+    uint32_t incl = wd;
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+      const uint32_t up = w.shfl(incl, (lane - d) & 31u);
+      if (lane >= d) incl += up;
+    }
+    const uint32_t total = w.shfl(incl, 31u);
+    if (wd) {
+      const uint32_t b = carry + incl - wd, word = b >> 5, o = b & 31u;
+      if (o + wd <= 32u) {
+        w.atomic_or(stage + word, code << (32u - o - wd));
+      } else {
+        w.atomic_or(stage + word, code >> (o + wd - 32u));
+        w.atomic_or(stage + word + 1u, code << (64u - o - wd));
+      }
+    }
+    w.sync();
+    const uint32_t pending = carry + total, full = pending >> 5;
+    const uint32_t v = lane < PE_STAGE ? stage[lane] : 0u;
+    const uint32_t part = w.shfl(v, full);
+    if (op + 4u * full <= cap) {
+      if (lane < full) *reinterpret_cast<uint32_t*>(out + op + 4u * lane) = bswap32(v);
+    } else {
+      overflow = true;
+    }
+    w.sync();
+    if (lane < PE_STAGE) stage[lane] = lane == 0u ? part : 0u;
+    w.sync();
+    op += 4u * full;
+    carry = pending & 31u;
+    obits += total;
+  }
+  LZW_HD void emit1(uint32_t code, int width) { emit(lane == 0u ? code : 0u, lane == 0u ? (uint32_t)width : 0u); }
+
+  LZW_HD void clear_table() {
+    w.sync();
+    uint64_t* t64 = reinterpret_cast<uint64_t*>(tab);
+    for (uint32_t i = lane; i < ENC_SLOTS / 2; i += 32u) t64[i] = ~0ull;
+    w.sync();
+  }
+};
+
+LZW_HD int width_for(uint32_t free_ent) {      // code width while free_ent entries + specials exist
+  return 9 + (free_ent >= 512u) + (free_ent >= 1024u) + (free_ent >= 2048u);
+}
+
+// in: n < 2^28 bytes; out: 4-byte aligned, cap bytes; table: ENC_SLOTS words; stage: PE_STAGE words.
+// Needs a full warp (W::n == 32).  Returns the strip's byte count or OVERFLOW.
+template <class W>
+LZW_HD uint32_t encode_strip_par(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* table,
+                                 uint32_t* stage, const W& w) {
+  ParEncoder<W> e(w);
+  const uint32_t lane = (uint32_t)w.lane;
+  e.lane = lane;
+  e.tab = table;
+  e.stage = stage;
+  e.out = out;
+  e.cap = cap & ~3u;
+  e.op = 0;
+  e.carry = 0;
+  e.obits = 0;
+  e.overflow = false;
+  uint32_t F = CODE_FIRST;          // free_ent
+  int nbits = BITS_MIN;
+  uint32_t in_base = 0, bits_base = 0, checkpoint = CHECK_GAP, ratio = 0;
+  if (lane < PE_STAGE) stage[lane] = 0;
+  e.clear_table();
+  const uint32_t lt = (1u << lane) - 1u;
+
+  auto reset = [&](uint32_t consumed) {       // libtiff: cl_hash, counters to zero, ClearCode at the old width
+    e.clear_table();
+    ratio = 0;
+    in_base = consumed;
+    bits_base = e.obits;
+    F = CODE_FIRST;
+    e.emit1(CODE_CLEAR, nbits);
+    nbits = BITS_MIN;
+  };
+
+  uint32_t ent = 0;
+  bool any = false;
+  if (n > 0) {
+    any = true;
+    e.emit1(CODE_CLEAR, nbits);
+    uint32_t x0 = 0;                // start of the next phrase
+    for (;;) {
+      // ---- every lane walks the dictionary from its own byte ---------------------------------
+      const uint32_t p = x0 + lane;
+      const bool active = p < n;
+      uint32_t node = active ? in[p] : 0u, d = 1, key = 0, h = 0;
+      bool done = !active, open = false, fresh = true;
+      while (w.ballot(!done)) {
+        if (!done) {
+          if (fresh) {
+            if (p + d >= n) {
+              open = true;               // ran into the end of the strip: the last phrase
+              done = true;
+            } else {
+              key = (node << 8) | in[p + d];
+              h = slot_of(key);
+              fresh = false;
+            }
+          }
+          if (!done) {
+            const uint32_t s = table[h];
+            if ((s >> 12) == key) {
+              node = s & 0xFFFu;
+              ++d;
+              fresh = true;
+            } else if (s == ENC_EMPTY) {
+              done = true;               // phrase = d bytes, fails on `key`, h is the free slot
+            } else {
+              h = h + 1u == ENC_SLOTS ? 0u : h + 1u;
+            }
+          }
+        }
+      }
+      // ---- phrase starts reachable from lane 0: pointer doubling -------------------------------
+      const uint32_t nxt = lane + d;                                   // window-relative end of this lane's phrase
+      uint32_t jump = (!active || open || nxt > 31u) ? 32u : nxt;
+      uint32_t reach = 1u;
+      for (int r = 0; r < 5; ++r) {
+        reach |= w.reduce_or((((reach >> lane) & 1u) && jump < 32u) ? (1u << jump) : 0u);
+        const uint32_t jj = w.shfl(jump, jump & 31u);
+        jump = jump < 32u ? jj : 32u;
+      }
+      const bool start = (reach >> lane) & 1u;
+      const uint32_t j = popc32(reach & lt);      // phrase index within the window
+      uint32_t m = popc32(reach);                // phrases to accept
+      // ---- where to cut ---------------------------------------------------------------------------
+      const uint32_t same = w.match_any((start && !open) ? key : (0x80000000u | lane));
+      const bool later_dup = start && !open && (same & lt) != 0u;     // an earlier phrase fails on the same pair
+      const uint32_t f1 = F + j + 1u;                                  // free_ent after this phrase's entry
+      const bool limit_ev = f1 == 512u || f1 == 1024u || f1 == 2048u || f1 == (uint32_t)CODE_MAX - 1u;
+      const bool reset_ev = f1 == (uint32_t)CODE_MAX - 1u;
+      const uint32_t consumed = p + d + 1u;                            // bytes consumed when the phrase fails
+      const bool ratio_ev = !limit_ev && consumed - in_base >= checkpoint;
+      const uint32_t before = w.ballot(start && (open || later_dup));
+      const uint32_t after = w.ballot(start && !open && !later_dup && (reset_ev || ratio_ev));
+      if (before) {
+        const uint32_t jb = popc32(reach & ((1u << ctz32(before)) - 1u));
+        if (jb < m) m = jb;
+      }
+      if (after) {
+        const uint32_t ja = popc32(reach & ((1u << ctz32(after)) - 1u)) + 1u;
+        if (ja < m) m = ja;
+      }
+      if (m == 0u) {                    // lane 0's phrase runs to the end of the strip
+        ent = w.shfl(node, 0u);
+        break;
+      }
+      // ---- accepted phrases: emit codes, insert entries ------------------------------------------------
+      const bool acc = start && j < m;
+      e.emit(node, acc ? (uint32_t)width_for(F + j) : 0u);
+      if (acc) {
+        const uint32_t val = (key << 12) | (F + j);
+        while (w.atomic_cas(table + h, (uint32_t)ENC_EMPTY, val) != (uint32_t)ENC_EMPTY) h = h + 1u == ENC_SLOTS ? 0u : h + 1u;
+      }
+      w.sync();
+      const uint32_t last = ctz32(w.ballot(acc && j == m - 1u));
+      x0 += w.shfl(nxt, last);
+      F += m;
+      nbits = width_for(F);
+      const uint32_t ev = w.shfl((reset_ev ? 1u : 0u) | (ratio_ev ? 2u : 0u), last);
+      const uint32_t cons = w.shfl(consumed, last);
+      if (ev & 1u) {
+        reset(cons);
+      } else if (ev & 2u) {
+        const uint32_t incount = cons - in_base, outcount = e.obits - bits_base;
+        checkpoint = incount + CHECK_GAP;
+        uint32_t rat;
+        if (incount > 0x007fffffu) {
+          rat = outcount >> 8;
+          rat = rat == 0 ? 0x7fffffffu : incount / rat;
+        } else {
+          rat = (incount << 8) / outcount;
+        }
+        if (rat <= ratio)
+          reset(cons);
+        else
+          ratio = rat;
+      }
+    }
+  }
+  // ---- LZWPostEncode ------------------------------------------------------------------------------
+  if (any) {
+    e.emit1(ent, nbits);
+    F++;
+    if (F == (uint32_t)CODE_MAX - 1u) {
+      e.emit1(CODE_CLEAR, nbits);
+      nbits = BITS_MIN;
+    } else if (F == 512u || F == 1024u || F == 2048u) {
+      nbits++;
+    }
+  }
+  e.emit1(CODE_EOI, nbits);
+  const uint32_t tail = (e.carry + 7u) >> 3;
+  if (e.op + tail <= cap) {
+    if (lane < tail) out[e.op + lane] = (uint8_t)(stage[0] >> (24u - 8u * lane));
+  } else {
+    e.overflow = true;
+  }
+  w.sync();
+  return e.overflow ? (uint32_t)OVERFLOW : e.op + tail;
 }
 
 // ------------------------------------------------------------------------------------------

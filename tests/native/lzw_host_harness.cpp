@@ -27,6 +27,27 @@ struct Warp32 {
     sh->bar.arrive_and_wait();
     return r;
   }
+  uint32_t reduce_or(uint32_t v) const {
+    sh->slot[lane] = v;
+    sh->bar.arrive_and_wait();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= sh->slot[i];
+    sh->bar.arrive_and_wait();
+    return r;
+  }
+  uint32_t match_any(uint32_t v) const {
+    sh->slot[lane] = v;
+    sh->bar.arrive_and_wait();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= (uint32_t)(sh->slot[i] == v) << i;
+    sh->bar.arrive_and_wait();
+    return r;
+  }
+  void atomic_or(uint32_t* p, uint32_t v) const { __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+  uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) const {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+  }
   uint32_t ballot(bool p) const {
     sh->slot[lane] = p ? 1u : 0u;
     sh->bar.arrive_and_wait();
@@ -46,6 +67,23 @@ uint32_t harness_encode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t ca
   const uint32_t r = ips_lzw::encode_strip(in, n, out, cap, table, w);
   free(table);
   return r;
+}
+uint32_t harness_encode_par(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap) {
+  uint32_t* table = (uint32_t*)aligned_alloc(16, ips_lzw::ENC_SLOTS * 4);
+  uint32_t* stage = (uint32_t*)aligned_alloc(16, ips_lzw::PE_STAGE * 4);
+  Shared sh;
+  uint32_t ret[32];
+  std::vector<std::thread> lanes;
+  for (int l = 0; l < 32; ++l)
+    lanes.emplace_back([&, l] {
+      Warp32 w{l, &sh};
+      ret[l] = ips_lzw::encode_strip_par(in, n, out, cap, table, stage, w);
+    });
+  for (auto& t : lanes) t.join();
+  free(table); free(stage);
+  for (int l = 1; l < 32; ++l)
+    if (ret[l] != ret[0]) return 0xFFFFFFFEu;   // the lanes must agree
+  return ret[0];
 }
 int harness_decode(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t n_out) {
   uint16_t* orel = (uint16_t*)aligned_alloc(16, ips_lzw::PD_TAB * 2);
