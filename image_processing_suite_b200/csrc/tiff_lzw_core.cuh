@@ -287,16 +287,10 @@ struct ParEncoder {
 
   LZW_HD ParEncoder(const W& w_) : w(w_) {}
 
-  // every lane contributes `wd` bits of `code` (wd == 0: nothing), in lane order
-  LZW_HD void emit(uint32_t code, uint32_t wd) {
-    uint32_t incl = wd;
-    for (uint32_t d = 1; d < 32u; d <<= 1) {
-      const uint32_t up = w.shfl(incl, (lane - d) & 31u);
-      if (lane >= d) incl += up;
-    }
-    const uint32_t total = w.shfl(incl, 31u);
+  // this lane's `wd` bits of `code` at bit offset `b` of the staged stream (wd == 0: nothing)
+  LZW_HD void place(uint32_t code, uint32_t wd, uint32_t b) {
     if (wd) {
-      const uint32_t b = carry + incl - wd, word = b >> 5, o = b & 31u;
+      const uint32_t word = b >> 5, o = b & 31u;
       if (o + wd <= 32u) {
         w.atomic_or(stage + word, code << (32u - o - wd));
       } else {
@@ -304,6 +298,9 @@ struct ParEncoder {
         w.atomic_or(stage + word + 1u, code << (64u - o - wd));
       }
     }
+  }
+  // `total` bits have been placed behind the carried ones: whole words go to global memory
+  LZW_HD void flush(uint32_t total) {
     w.sync();
     const uint32_t pending = carry + total, full = pending >> 5;
     const uint32_t v = lane < PE_STAGE ? stage[lane] : 0u;
@@ -320,7 +317,25 @@ struct ParEncoder {
     carry = pending & 31u;
     obits += total;
   }
-  LZW_HD void emit1(uint32_t code, int width) { emit(lane == 0u ? code : 0u, lane == 0u ? (uint32_t)width : 0u); }
+  // bits of the first j codes of a window that starts with free_ent == F: 9 each, one more for
+  // every code emitted while free_ent >= 512, 1024, 2048
+  static LZW_HD uint32_t bits_before(uint32_t j, uint32_t F) {
+    uint32_t b = 9u * j;
+    for (uint32_t T = 512u; T <= 2048u; T <<= 1) {
+      const int over = (int)(F + j) - (int)T;          // codes i < j with F + i >= T: clamp(F + j - T, 0, j)
+      b += over <= 0 ? 0u : ((uint32_t)over < j ? (uint32_t)over : j);
+    }
+    return b;
+  }
+  // the codes of the m accepted phrases of a window (this lane: phrase j if acc)
+  LZW_HD void emit_phrases(uint32_t code, bool acc, uint32_t j, uint32_t m, uint32_t F) {
+    place(code, acc ? (uint32_t)(9 + (F + j >= 512u) + (F + j >= 1024u) + (F + j >= 2048u)) : 0u, carry + bits_before(j, F));
+    flush(bits_before(m, F));
+  }
+  LZW_HD void emit1(uint32_t code, int width) {       // one code, uniform arguments
+    place(code, lane == 0u ? (uint32_t)width : 0u, carry);
+    flush((uint32_t)width);
+  }
 
   LZW_HD void clear_table() {
     w.sync();
@@ -375,36 +390,46 @@ LZW_HD uint32_t encode_strip_par(const uint8_t* in, uint32_t n, uint8_t* out, ui
     uint32_t x0 = 0;                // start of the next phrase
     for (;;) {
       // ---- every lane walks the dictionary from its own byte ---------------------------------
+      // st: 0 walking, 1 the phrase of d bytes fails on `key` (h is the free slot), 2 ran into the
+      // end of the strip (the last phrase) or lies beyond it.  One probe per iteration; the next
+      // input byte is loaded one step ahead of its use.
       const uint32_t p = x0 + lane;
       const bool active = p < n;
-      uint32_t node = active ? in[p] : 0u, d = 1, key = 0, h = 0;
-      bool done = !active, open = false, fresh = true;
-      while (w.ballot(!done)) {
-        if (!done) {
-          if (fresh) {
-            if (p + d >= n) {
-              open = true;               // ran into the end of the strip: the last phrase
-              done = true;
-            } else {
-              key = (node << 8) | in[p + d];
-              h = slot_of(key);
-              fresh = false;
-            }
-          }
-          if (!done) {
-            const uint32_t s = table[h];
-            if ((s >> 12) == key) {
-              node = s & 0xFFFu;
-              ++d;
-              fresh = true;
-            } else if (s == ENC_EMPTY) {
-              done = true;               // phrase = d bytes, fails on `key`, h is the free slot
-            } else {
-              h = h + 1u == ENC_SLOTS ? 0u : h + 1u;
-            }
-          }
+      uint32_t node = 0, d = 1, key = 0, h = 0, ahead = 0, st = 2;
+      if (active) {
+        node = in[p];
+        if (p + 1u < n) {
+          key = (node << 8) | in[p + 1u];
+          h = slot_of(key);
+          st = 0;
+          if (p + 2u < n) ahead = in[p + 2u];
         }
       }
+      auto probe = [&]() {
+        if (st == 0u) {
+          const uint32_t s = table[h];
+          if ((s >> 12) == key) {
+            node = s & 0xFFFu;
+            ++d;
+            if (p + d >= n) {
+              st = 2;
+            } else {
+              key = (node << 8) | ahead;
+              h = slot_of(key);
+              if (p + d + 1u < n) ahead = in[p + d + 1u];
+            }
+          } else if (s == ENC_EMPTY) {
+            st = 1;
+          } else {
+            h = h + 1u == ENC_SLOTS ? 0u : h + 1u;
+          }
+        }
+      };
+      while (w.ballot(st == 0u)) {
+        probe();
+        probe();
+      }
+      const bool open = active && st == 2u;
       // ---- phrase starts reachable from lane 0: pointer doubling -------------------------------
       const uint32_t nxt = lane + d;                                   // window-relative end of this lane's phrase
       uint32_t jump = (!active || open || nxt > 31u) ? 32u : nxt;
@@ -435,24 +460,28 @@ LZW_HD uint32_t encode_strip_par(const uint8_t* in, uint32_t n, uint8_t* out, ui
         const uint32_t ja = popc32(reach & ((1u << ctz32(after)) - 1u)) + 1u;
         if (ja < m) m = ja;
       }
+#ifdef LZW_STATS
+      if (lane == 0) lzw_stats(m, popc32(reach), before, after);
+#endif
       if (m == 0u) {                    // lane 0's phrase runs to the end of the strip
         ent = w.shfl(node, 0u);
         break;
       }
       // ---- accepted phrases: emit codes, insert entries ------------------------------------------------
       const bool acc = start && j < m;
-      e.emit(node, acc ? (uint32_t)width_for(F + j) : 0u);
+      e.emit_phrases(node, acc, j, m, F);
       if (acc) {
         const uint32_t val = (key << 12) | (F + j);
         while (w.atomic_cas(table + h, (uint32_t)ENC_EMPTY, val) != (uint32_t)ENC_EMPTY) h = h + 1u == ENC_SLOTS ? 0u : h + 1u;
       }
       w.sync();
       const uint32_t last = ctz32(w.ballot(acc && j == m - 1u));
-      x0 += w.shfl(nxt, last);
+      const uint32_t tail = w.shfl(nxt | (reset_ev ? 0x10000u : 0u) | (ratio_ev ? 0x20000u : 0u), last);
+      x0 += tail & 0xFFFFu;                                            // nxt <= 31 + 3839
+      const uint32_t cons = x0 + 1u;                                   // = consumed of the last accepted phrase
+      const uint32_t ev = tail >> 16;
       F += m;
       nbits = width_for(F);
-      const uint32_t ev = w.shfl((reset_ev ? 1u : 0u) | (ratio_ev ? 2u : 0u), last);
-      const uint32_t cons = w.shfl(consumed, last);
       if (ev & 1u) {
         reset(cons);
       } else if (ev & 2u) {
