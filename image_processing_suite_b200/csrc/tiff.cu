@@ -5,8 +5,9 @@
 // ips_tiff_lzw_encode_u16: uint16 planes in HBM -> complete little-endian TIFF files in HBM,
 // byte-identical to what Pillow 12.2 / libtiff 4.7 writes for the same pixels (strip LZW
 // streams, strip size, tag set and placement), so only compressed bytes cross PCIe.
-//   1. tiff_lzw_encode_kernel   one warp per strip, hash table in 21.5 KB of shared memory,
-//                               strips land in fixed-capacity slots of the workspace;
+//   1. tiff_lzw_encode_kernel   one warp per strip, 32 bytes per step (one speculative dictionary
+//                               walk per lane), hash table in 21.5 KB of shared memory, strips
+//                               land in fixed-capacity slots of the workspace;
 //   2. tiff_layout_kernel       one CTA per plane: scan of the strip sizes -> offsets, header,
 //                               IFD and the two strip arrays written behind the strips;
 //   3. tiff_gather_kernel       one CTA per strip: slot -> its place in the file.
@@ -15,9 +16,9 @@
 // an 8 KB output window in shared memory, written out in 16-byte vectors (tiff_lzw_core.cuh).
 // ips_tiff_fix_u16 undoes big-endian samples and horizontal differencing (Predictor = 2).
 //
-// The encoder is a serial state machine per strip, bound by the latency of one shared-memory
-// probe per byte, not by HBM; its parallelism is strips x planes (36 strips per 1080^2 plane,
-// 180 per 5-channel field), 10 resident warps per SM.
+// Both directions are bound by dependent shared-memory / shuffle latency on one warp per strip,
+// not by HBM (DRAM traffic is the data once); throughput scales with the resident strips
+// (10 encoder or 13 decoder warps per SM) x planes x strips (36 per 1080^2 plane).
 #include "ips_common.cuh"
 #include "tiff_lzw_core.cuh"
 
@@ -36,7 +37,7 @@ tiff_lzw_encode_kernel(const uint8_t* __restrict__ planes, uint8_t* __restrict__
   const uint8_t* in = planes + (size_t)p * plane_bytes + (size_t)r0 * row_bytes;
   const size_t slot = (size_t)p * S + s;
   lz::Warp w;
-  const uint32_t n = lz::encode_strip_par(in, (uint32_t)rows * row_bytes, slots + slot * cap, cap, table, stage, w);
+  const uint32_t n = lz::encode_strip(in, (uint32_t)rows * row_bytes, slots + slot * cap, cap, table, stage, w);
   if (w.lane == 0) strip_bytes[slot] = n;
 }
 

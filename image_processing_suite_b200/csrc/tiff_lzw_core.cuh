@@ -1,7 +1,7 @@
 // TIFF LZW strip coder, shared between the CUDA kernels of tiff.cu and the host harness of
-// tests/native/lzw_host_harness.cpp (which compiles this header with g++ -- the encoder with a
-// 1-lane "warp", the decoder with 32 threads standing in for the lanes -- to check the very
-// code the kernels run against Pillow/libtiff on the CPU-only authoring box).
+// tests/native/lzw_host_harness.cpp (which compiles this header with g++, 32 threads standing in
+// for the lanes and a barrier for the warp collectives, to check the very code the kernels run
+// against Pillow/libtiff on the CPU-only authoring box).
 //
 // The stream format is TIFF 6.0 section 13 as libtiff writes it (the codec behind
 // img.save(..., compression='tiff_lzw'), Image_re-binning.py:19-21): MSB-first codes of 9..12
@@ -10,11 +10,8 @@
 // Following that policy to the letter makes the strips byte-identical to libtiff's, so the
 // files can be compared with cmp, not only decoded.
 //
-// Execution model: one warp per strip.  Encoding is a serial state machine (the next match
-// starts where the previous one ended), so every lane runs the same instruction stream on the
-// same values (shared-memory reads broadcast, identical writes collapse), only lane 0 stores to
-// global memory and the lanes share the one job that parallelises, clearing the 21.5 KB hash
-// table.  Decoding is parallel across the lanes (see the decoder below).
+// Execution model: one warp per strip, the 32 lanes working on 32 consecutive bytes (encoder) or
+// 32 consecutive codes (decoder) at a time; see the two sections below.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -55,11 +52,7 @@ LZW_HD void copy16(uint8_t* dst, const uint8_t* src) {
   *reinterpret_cast<Vec16*>(dst) = *reinterpret_cast<const Vec16*>(src);
 }
 #else
-struct Warp {
-  int lane = 0;
-  static constexpr int n = 1;
-  void sync() const {}
-};
+// the host build supplies its own warp type (32 threads, tests/native/lzw_host_harness.cpp)
 inline uint32_t ctz32(uint32_t v) { return (uint32_t)__builtin_ctz(v); }
 inline uint32_t popc32(uint32_t v) { return (uint32_t)__builtin_popcount(v); }
 inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
@@ -74,194 +67,14 @@ static inline size_t encode_bound(size_t n) { return (n + n / 2 + n / 1024 + 64 
 // ------------------------------------------------------------------------------------------
 // encoder
 // ------------------------------------------------------------------------------------------
-// One byte costs one dependent chain  key -> hash -> shared-memory probe -> compare  (the warp
-// has nothing else to overlap it with), so the bookkeeping libtiff does per byte is folded into
-// quantities that only change on a table miss: incount = consumed - in_base, outcount =
-// bits emitted - bits_base, and the "code width grows / table full" tests share one compare.
+// Dictionary: open addressing in shared memory, slot = (key << 12) | code with key = (prefix code
+// << 8) | byte, linear probing, all-ones = empty.
 #ifdef __CUDACC__
 LZW_HD uint32_t slot_of(uint32_t key) { return __umulhi(key * 0x9E3779B1u, (uint32_t)ENC_SLOTS); }
 #else
 inline uint32_t slot_of(uint32_t key) { return (uint32_t)(((uint64_t)(key * 0x9E3779B1u) * ENC_SLOTS) >> 32); }
 #endif
 
-struct Encoder {
-  uint32_t* tab;     // [ENC_SLOTS] (key << 12) | code, key = (prefix code << 8) | byte
-  uint8_t* out;      // 4-byte aligned
-  uint32_t cap;      // multiple of 4
-  uint32_t op;       // bytes written (multiple of 4 until finish())
-  uint32_t acc;      // low nacc (< 32) bits are pending output; bits above them are stale
-  int nacc;
-  int nbits;
-  uint32_t limit;    // free_ent at which the next width change (512, 1024, 2048) or the reset (4094) happens
-  uint32_t free_ent, ent;
-  uint32_t in_base, bits_base, checkpoint, ratio;
-  bool overflow;
-  int lane;
-
-  LZW_HD void put(uint32_t code) {
-    const int t = nacc + nbits;
-    if (t >= 32) {
-      const int r = t - 32;                                    // low bits of `code` that stay pending
-      const uint32_t word = (acc << (nbits - r)) | (code >> r);
-      acc = code;
-      nacc = r;
-      if (op + 4 <= cap) {
-        if (lane == 0) *reinterpret_cast<uint32_t*>(out + op) = bswap32(word);
-        op += 4;
-      } else {
-        overflow = true;
-      }
-    } else {
-      acc = (acc << nbits) | code;
-      nacc = t;
-    }
-  }
-
-  template <class W>
-  LZW_HD void clear_table(const W& w) {
-    w.sync();
-    uint64_t* t64 = reinterpret_cast<uint64_t*>(tab);
-#pragma unroll 4
-    for (uint32_t i = w.lane; i < ENC_SLOTS / 2; i += W::n) t64[i] = ~0ull;
-    w.sync();
-  }
-
-  // libtiff: cl_hash, ratio = incount = outcount = 0, CODE_CLEAR at the old width, 9-bit codes
-  template <class W>
-  LZW_HD void reset(uint32_t consumed, const W& w) {
-    clear_table(w);
-    ratio = 0;
-    in_base = consumed;
-    bits_base = op * 8u + (uint32_t)nacc;
-    free_ent = CODE_FIRST;
-    put(CODE_CLEAR);
-    nbits = BITS_MIN;
-    limit = 1u << BITS_MIN;
-  }
-
-  template <class W>
-  LZW_HD void begin(uint32_t* table, uint8_t* dst, uint32_t capacity, const W& w) {
-    tab = table;
-    out = dst;
-    cap = capacity & ~3u;
-    op = 0;
-    acc = 0;
-    nacc = 0;
-    nbits = BITS_MIN;
-    limit = 1u << BITS_MIN;
-    free_ent = CODE_FIRST;
-    ent = 0;
-    in_base = 0;
-    bits_base = 0;
-    checkpoint = CHECK_GAP;
-    ratio = 0;
-    overflow = false;
-    lane = w.lane;
-    clear_table(w);
-  }
-
-  // c is the consumed-th byte of the strip (1-based), not the first
-  template <class W>
-  LZW_HD void byte(uint32_t c, uint32_t consumed, const W& w) {
-    const uint32_t key = (ent << 8) | c;
-    uint32_t h = slot_of(key);
-    for (;;) {
-      const uint32_t s = tab[h];
-      if ((s >> 12) == key) {
-        ent = s & 0xFFFu;
-        return;
-      }
-      if (s == ENC_EMPTY) break;
-      h = h + 1 == ENC_SLOTS ? 0u : h + 1;
-    }
-    put(ent);
-    ent = c;
-    tab[h] = (key << 12) | free_ent;
-    free_ent++;
-    if (free_ent == limit) {
-      if (limit == (uint32_t)CODE_MAX - 1) {
-        reset(consumed, w);
-      } else {
-        nbits++;
-        limit = limit == 2048u ? (uint32_t)CODE_MAX - 1 : limit << 1;
-      }
-    } else if (consumed - in_base >= checkpoint) {
-      const uint32_t incount = consumed - in_base;
-      const uint32_t outcount = op * 8u + (uint32_t)nacc - bits_base;
-      checkpoint = incount + CHECK_GAP;
-      uint32_t rat;
-      if (incount > 0x007fffffu) {
-        rat = outcount >> 8;
-        rat = rat == 0 ? 0x7fffffffu : incount / rat;
-      } else {
-        rat = (incount << 8) / outcount;
-      }
-      if (rat <= ratio)
-        reset(consumed, w);
-      else
-        ratio = rat;
-    }
-  }
-
-  // LZWPostEncode; returns the strip's byte count or OVERFLOW
-  LZW_HD uint32_t finish(bool any) {
-    if (any) {
-      put(ent);
-      free_ent++;
-      if (free_ent == (uint32_t)CODE_MAX - 1) {
-        put(CODE_CLEAR);
-        nbits = BITS_MIN;
-      } else if (free_ent == limit) {
-        nbits++;
-      }
-    }
-    put(CODE_EOI);
-    while (nacc > 0) {
-      const uint32_t b = nacc >= 8 ? (acc >> (nacc - 8)) & 0xFFu : (acc << (8 - nacc)) & 0xFFu;
-      nacc -= 8;
-      if (op < cap) {
-        if (lane == 0) out[op] = (uint8_t)b;
-        op++;
-      } else {
-        overflow = true;
-      }
-    }
-    return overflow ? (uint32_t)OVERFLOW : op;
-  }
-};
-
-// in: n < 2^28 bytes (any alignment); out: 4-byte aligned, cap bytes; table: ENC_SLOTS words
-template <class W>
-LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* table, const W& w) {
-  Encoder e;
-  e.begin(table, out, cap, w);
-  if (n == 0) return e.finish(false);
-  e.put(CODE_CLEAR);
-  e.ent = in[0];
-  uint32_t i = 1;
-  while (i < n && (reinterpret_cast<uintptr_t>(in + i) & 3u)) {      // up to the first aligned word
-    e.byte(in[i], i + 1, w);
-    ++i;
-  }
-  if (i + 4u <= n) {
-    uint32_t next = load_u32(in + i);            // one word of look-ahead keeps the load off the chain
-#pragma unroll 1
-    for (; i + 4u <= n; i += 4u) {
-      const uint32_t cur = next;
-      if (i + 8u <= n) next = load_u32(in + i + 4u);
-      e.byte(cur & 0xFFu, i + 1, w);
-      e.byte((cur >> 8) & 0xFFu, i + 2, w);
-      e.byte((cur >> 16) & 0xFFu, i + 3, w);
-      e.byte(cur >> 24, i + 4, w);
-    }
-  }
-  for (; i < n; ++i) e.byte(in[i], i + 1, w);
-  return e.finish(true);
-}
-
-// ------------------------------------------------------------------------------------------
-// lane-parallel encoder
-// ------------------------------------------------------------------------------------------
 // Greedy LZW parsing is serial only through the phrase boundaries.  Each lane therefore walks the
 // dictionary from its own byte of a 32-byte window as if a phrase started there; the boundaries
 // are then found by pointer doubling over "start + length" (five shuffle rounds), and every lane
@@ -352,7 +165,7 @@ LZW_HD int width_for(uint32_t free_ent) {      // code width while free_ent entr
 // in: n < 2^28 bytes; out: 4-byte aligned, cap bytes; table: ENC_SLOTS words; stage: PE_STAGE words.
 // Needs a full warp (W::n == 32).  Returns the strip's byte count or OVERFLOW.
 template <class W>
-LZW_HD uint32_t encode_strip_par(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* table,
+LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* table,
                                  uint32_t* stage, const W& w) {
   ParEncoder<W> e(w);
   const uint32_t lane = (uint32_t)w.lane;
@@ -428,6 +241,8 @@ LZW_HD uint32_t encode_strip_par(const uint8_t* in, uint32_t n, uint8_t* out, ui
       while (w.ballot(st == 0u)) {
         probe();
         probe();
+        probe();
+        probe();
       }
       const bool open = active && st == 2u;
       // ---- phrase starts reachable from lane 0: pointer doubling -------------------------------
@@ -460,9 +275,6 @@ LZW_HD uint32_t encode_strip_par(const uint8_t* in, uint32_t n, uint8_t* out, ui
         const uint32_t ja = popc32(reach & ((1u << ctz32(after)) - 1u)) + 1u;
         if (ja < m) m = ja;
       }
-#ifdef LZW_STATS
-      if (lane == 0) lzw_stats(m, popc32(reach), before, after);
-#endif
       if (m == 0u) {                    // lane 0's phrase runs to the end of the strip
         ent = w.shfl(node, 0u);
         break;

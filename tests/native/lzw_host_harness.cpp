@@ -1,6 +1,6 @@
-// Host build of the LZW strip coder of image_processing_suite_b200/csrc/tiff_lzw_core.cuh: the
-// encoder with a 1-lane "warp", the decoder with 32 threads standing in for the 32 lanes
-// (ballot / shuffle / syncwarp through a barrier).  Lets the CPU-only suite check the code the
+// Host build of the LZW strip coder of image_processing_suite_b200/csrc/tiff_lzw_core.cuh with 32
+// threads standing in for the 32 lanes (ballot / shuffle / match / reduce / syncwarp through a
+// barrier, shared-memory atomics through __atomic builtins).  Lets the CPU-only suite check the code the
 // CUDA kernels run against Pillow/libtiff.  Test infrastructure only; libips.so does not
 // contain this code path.
 #include <stdint.h>
@@ -63,13 +63,6 @@ extern "C" {
 uint64_t harness_bound(uint64_t n) { return ips_lzw::encode_bound(n); }
 uint32_t harness_encode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap) {
   uint32_t* table = (uint32_t*)aligned_alloc(16, ips_lzw::ENC_SLOTS * 4);
-  ips_lzw::Warp w;
-  const uint32_t r = ips_lzw::encode_strip(in, n, out, cap, table, w);
-  free(table);
-  return r;
-}
-uint32_t harness_encode_par(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap) {
-  uint32_t* table = (uint32_t*)aligned_alloc(16, ips_lzw::ENC_SLOTS * 4);
   uint32_t* stage = (uint32_t*)aligned_alloc(16, ips_lzw::PE_STAGE * 4);
   Shared sh;
   uint32_t ret[32];
@@ -77,7 +70,7 @@ uint32_t harness_encode_par(const uint8_t* in, uint32_t n, uint8_t* out, uint32_
   for (int l = 0; l < 32; ++l)
     lanes.emplace_back([&, l] {
       Warp32 w{l, &sh};
-      ret[l] = ips_lzw::encode_strip_par(in, n, out, cap, table, stage, w);
+      ret[l] = ips_lzw::encode_strip(in, n, out, cap, table, stage, w);
     });
   for (auto& t : lanes) t.join();
   free(table); free(stage);
