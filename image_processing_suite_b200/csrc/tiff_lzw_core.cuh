@@ -40,6 +40,7 @@ struct Warp {
   __device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(0xffffffffu, v, (int)src); }
   __device__ __forceinline__ uint32_t reduce_or(uint32_t v) const { return __reduce_or_sync(0xffffffffu, v); }
   __device__ __forceinline__ uint32_t match_any(uint32_t v) const { return __match_any_sync(0xffffffffu, v); }
+  __device__ __forceinline__ void prefetch(const void* p) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
   __device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) const { atomicOr(p, v); }
   __device__ __forceinline__ uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) const { return atomicCAS(p, cmp, v); }
 };
@@ -208,6 +209,7 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
       // input byte is loaded one step ahead of its use.
       const uint32_t p = x0 + lane;
       const bool active = p < n;
+      if (lane == 0u && x0 + 384u < n) w.prefetch(in + x0 + 384u);     // the input line three windows ahead
       uint32_t node = 0, d = 1, key = 0, h = 0, ahead = 0, st = 2;
       if (active) {
         node = in[p];
@@ -245,6 +247,9 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
         probe();
       }
       const bool open = active && st == 2u;
+      // lanes failing on the same (node, byte) pair; issued here so that its latency hides behind the
+      // doubling rounds below
+      const uint32_t same = w.match_any(st == 1u ? key : (0x80000000u | lane));
       // ---- phrase starts reachable from lane 0: pointer doubling -------------------------------
       const uint32_t nxt = lane + d;                                   // window-relative end of this lane's phrase
       uint32_t jump = (!active || open || nxt > 31u) ? 32u : nxt;
@@ -258,8 +263,7 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
       const uint32_t j = popc32(reach & lt);      // phrase index within the window
       uint32_t m = popc32(reach);                // phrases to accept
       // ---- where to cut ---------------------------------------------------------------------------
-      const uint32_t same = w.match_any((start && !open) ? key : (0x80000000u | lane));
-      const bool later_dup = start && !open && (same & lt) != 0u;     // an earlier phrase fails on the same pair
+      const bool later_dup = start && st == 1u && (same & reach & lt) != 0u;   // an earlier phrase fails on the same pair
       const uint32_t f1 = F + j + 1u;                                  // free_ent after this phrase's entry
       const bool limit_ev = f1 == 512u || f1 == 1024u || f1 == 2048u || f1 == (uint32_t)CODE_MAX - 1u;
       const bool reset_ev = f1 == (uint32_t)CODE_MAX - 1u;

@@ -43,6 +43,7 @@ struct Warp32 {
     sh->bar.arrive_and_wait();
     return r;
   }
+  void prefetch(const void*) const {}
   void atomic_or(uint32_t* p, uint32_t v) const { __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
   uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) const {
     __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
