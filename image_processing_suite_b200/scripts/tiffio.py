@@ -146,6 +146,8 @@ def decode_to_device(files, device=None):
         status = ops.tiff_lzw_decode(src, so, sb, dst, do, db)
         if int(status.max()) != 0:
             bad = int(torch.nonzero(status)[0])
+            if int(status[bad]) == 3:
+                raise Unsupported("pre-6.0 (LSB-first) LZW strip")          # libtiff still reads those: host decode
             raise ValueError("LZW strip %d is damaged (status %d)" % (bad, int(status[bad])))
     for p, i in enumerate(infos):
         if i["big_endian"] or i["predictor"] == 2:

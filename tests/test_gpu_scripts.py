@@ -32,7 +32,11 @@ def test_max_projection_script(tmp_path, monkeypatch):
         for p in range(Z):                                   # plane-major, channel-minor rows
             for j in range(C):
                 name = f"f{field}p{p}c{j}.tiff"
-                s3.upload_fileobj(io.BytesIO(tiffio.encode(st[j, p])), "img", f"exp/Images/{name}")
+                # per channel group: raw strips (with one LZW plane mixed in), LZW (device codec), deflate (host decode)
+                comp = (None, "tiff_lzw", "tiff_adobe_deflate")[(field + j) % 3]
+                if comp is None and p == 1:
+                    comp = "tiff_lzw"
+                s3.upload_fileobj(io.BytesIO(tiffio.encode(st[j, p], comp)), "img", f"exp/Images/{name}")
                 rows.append({"PlateID": "P1", "Image_PathName": "exp/Images", "Image_FileName": name})
     rows.append({"PlateID": "P1", "Image_PathName": "exp/Images", "Image_FileName": "tail.tiff"})   # incomplete chunk
     csv_bytes = pd.DataFrame(rows).to_csv(index=False, sep=";").encode()
