@@ -12,6 +12,7 @@
 // (the device sin() is not bit-identical to glibc's), cached per (in, out) size and uploaded
 // into the caller's workspace on the call's stream.
 #include <math.h>
+#include <string.h>
 
 #include <map>
 #include <mutex>
@@ -26,6 +27,9 @@ struct LanczosCoeffs {
   int ksize = 0;
   std::vector<int> bounds;    // [out][2]: first input index, tap count
   std::vector<double> kk;     // [out][ksize]
+  // Integer decimation: outputs [u_lo, u_hi) all use the same `u_taps` weights (bit for bit) on
+  // windows that advance by `u_step` input pixels: first input of output o is u_base + u_step * o.
+  int u_lo = 0, u_hi = 0, u_step = 0, u_taps = 0, u_base = 0;
 };
 
 static double sinc_pi(double x) {
@@ -68,6 +72,32 @@ static LanczosCoeffs make_coeffs(int in_size, int out_size) {
     c.bounds[(size_t)xx * 2] = xmin;
     c.bounds[(size_t)xx * 2 + 1] = n;
   }
+  // longest run of outputs with identical weights and evenly advancing windows (checked, not assumed)
+  if (in_size % out_size == 0 && in_size / out_size >= 2) {
+    const int step = in_size / out_size;
+    int best_lo = 0, best_hi = 0;
+    for (int lo = 0; lo < out_size;) {
+      int hi = lo + 1;
+      const int n0 = c.bounds[(size_t)lo * 2 + 1];
+      const double* k0 = &c.kk[(size_t)lo * c.ksize];
+      while (hi < out_size && c.bounds[(size_t)hi * 2 + 1] == n0 &&
+             c.bounds[(size_t)hi * 2] == c.bounds[(size_t)lo * 2] + step * (hi - lo) &&
+             memcmp(&c.kk[(size_t)hi * c.ksize], k0, (size_t)n0 * sizeof(double)) == 0)
+        ++hi;
+      if (hi - lo > best_hi - best_lo) {
+        best_lo = lo;
+        best_hi = hi;
+      }
+      lo = hi;
+    }
+    if (best_hi - best_lo >= 64) {
+      c.u_lo = best_lo;
+      c.u_hi = best_hi;
+      c.u_step = step;
+      c.u_taps = c.bounds[(size_t)best_lo * 2 + 1];
+      c.u_base = c.bounds[(size_t)best_lo * 2] - step * best_lo;
+    }
+  }
   return c;
 }
 
@@ -92,10 +122,10 @@ __device__ __forceinline__ uint16_t pil_store_u16(double ss) {
 __global__ void __launch_bounds__(256)
 lanczos_h_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                  const int* __restrict__ bounds, const double* __restrict__ kk, int ksize, int H,
-                 int W, int OW) {
-  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+                 int W, int OW, int x_begin, int x_end) {
+  const int xx = x_begin + blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, p = blockIdx.z;
-  if (xx >= OW) return;
+  if (xx >= x_end) return;
   const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
   const double* k = kk + (size_t)xx * ksize;
   const uint16_t* row = in + ((size_t)p * H + y) * W + xmin;
@@ -108,9 +138,9 @@ lanczos_h_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
 __global__ void __launch_bounds__(256)
 lanczos_v_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                  const int* __restrict__ bounds, const double* __restrict__ kk, int ksize, int H,
-                 int W, int OH) {
+                 int W, int OH, int y_begin) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int yy = blockIdx.y, p = blockIdx.z;
+  const int yy = y_begin + blockIdx.y, p = blockIdx.z;
   if (x >= W) return;
   const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
   const double* k = kk + (size_t)yy * ksize;
@@ -217,6 +247,91 @@ lanczos_v_staged_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ 
   }
 }
 
+
+// ---- integer decimation (2160 -> 1080 / 540, the script's resolutions) -------------------------
+// When every interior output uses the same TAPS weights on windows STEP pixels apart
+// (LanczosCoeffs::u_*, verified on the host), the weights live in registers and each input pixel
+// is loaded and converted once: a thread walks its NO * STEP + TAPS - STEP inputs in order and
+// adds pixel * weight into every output whose window holds it -- per output the same products
+// in the same order as the generic kernels, so the results are bit-identical.  No shared memory;
+// HBM sees the input and the output once.
+template <int STEP, int TAPS>
+struct LzWeights {
+  double w[TAPS];
+};
+
+// rows: thread = NO consecutive outputs of one row; lanes side by side along the row
+template <int STEP, int TAPS, int NO>
+__global__ void __launch_bounds__(128)
+lanczos_h_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzWeights<STEP, TAPS> wt, int H,
+                         int W, int OW, int u_lo, int u_base, int groups) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, p = blockIdx.z;
+  if (g >= groups) return;
+  const int o0 = u_lo + g * NO;
+  const uint16_t* src = in + ((size_t)p * H + y) * W + u_base + STEP * o0;
+  constexpr int NIN = NO * STEP + TAPS - STEP;
+  double ss[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) ss[o] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) {
+    const double px = (double)src[i];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      const int t = i - STEP * o;
+      if (t >= 0 && t < TAPS) ss[o] = __dadd_rn(ss[o], __dmul_rn(px, wt.w[t]));
+    }
+  }
+  uint16_t* dst = out + ((size_t)p * H + y) * OW + o0;
+#pragma unroll
+  for (int o = 0; o < NO; ++o) dst[o] = pil_store_u16(ss[o]);
+}
+
+// columns: thread = NO consecutive output rows of two adjacent columns; lanes side by side along the row
+template <int STEP, int TAPS, int NO>
+__global__ void __launch_bounds__(128)
+lanczos_v_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzWeights<STEP, TAPS> wt, int H,
+                         int W, int OH, int u_lo, int u_base) {
+  const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int p = blockIdx.z;
+  if (x >= W) return;
+  const int o0 = u_lo + blockIdx.y * NO;
+  const bool pair = x + 1 < W;
+  const uint16_t* src = in + ((size_t)p * H + u_base + STEP * o0) * W + x;
+  constexpr int NIN = NO * STEP + TAPS - STEP;
+  double s0[NO], s1[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) s0[o] = s1[o] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) {
+    const uint16_t* q = src + (size_t)i * W;
+    double a, b = 0.0;
+    if (pair && ((reinterpret_cast<uintptr_t>(q) & 3u) == 0)) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(q);
+      a = (double)(v & 0xFFFFu);
+      b = (double)(v >> 16);
+    } else {
+      a = (double)q[0];
+      if (pair) b = (double)q[1];
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      const int t = i - STEP * o;
+      if (t >= 0 && t < TAPS) {
+        s0[o] = __dadd_rn(s0[o], __dmul_rn(a, wt.w[t]));
+        s1[o] = __dadd_rn(s1[o], __dmul_rn(b, wt.w[t]));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    uint16_t* dst = out + ((size_t)p * OH + o0 + o) * W + x;
+    dst[0] = pil_store_u16(s0[o]);
+    if (pair) dst[1] = pil_store_u16(s1[o]);
+  }
+}
+
 // largest input span any block of `per_block` consecutive outputs needs
 static int lanczos_span_max(const LanczosCoeffs& c, int n_out, int per_block) {
   int m = 1;
@@ -247,6 +362,71 @@ static LanczosLayout lanczos_layout(int C, int H, int W, int OH, int OW) {
   L.vk = o; o += round_up((size_t)OH * kh * sizeof(double), 256);
   L.total = o;
   return L;
+}
+
+
+template <int STEP, int TAPS>
+static LzWeights<STEP, TAPS> uniform_weights(const LanczosCoeffs& c) {
+  LzWeights<STEP, TAPS> w;
+  for (int t = 0; t < TAPS; ++t) w.w[t] = c.kk[(size_t)c.u_lo * c.ksize + t];
+  return w;
+}
+
+// interior outputs through the register kernel, edges through the simple kernel; false = not applicable
+template <int STEP, int TAPS, int NO>
+static bool uniform_h_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk,
+                             int C, int H, int W, int OW, cudaStream_t st) {
+  const int groups = (c.u_hi - c.u_lo) / NO;
+  if (groups <= 0 || H > 65535) return false;
+  const int done_hi = c.u_lo + groups * NO;
+  lanczos_h_uniform_kernel<STEP, TAPS, NO><<<dim3((groups + 127) / 128, H, C), 128, 0, st>>>(
+      in, out, uniform_weights<STEP, TAPS>(c), H, W, OW, c.u_lo, c.u_base, groups);
+  count_launch();
+  if (c.u_lo > 0) {
+    lanczos_h_kernel<<<dim3((c.u_lo + 255) / 256, H, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OW, 0, c.u_lo);
+    count_launch();
+  }
+  if (done_hi < OW) {
+    lanczos_h_kernel<<<dim3((OW - done_hi + 255) / 256, H, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OW, done_hi, OW);
+    count_launch();
+  }
+  return true;
+}
+
+template <int STEP, int TAPS, int NO>
+static bool uniform_v_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk,
+                             int C, int H, int W, int OH, cudaStream_t st) {
+  const int groups = (c.u_hi - c.u_lo) / NO;
+  if (groups <= 0 || groups > 65535) return false;
+  const int done_hi = c.u_lo + groups * NO;
+  const int pairs = (W + 1) / 2;
+  lanczos_v_uniform_kernel<STEP, TAPS, NO><<<dim3((pairs + 127) / 128, groups, C), 128, 0, st>>>(
+      in, out, uniform_weights<STEP, TAPS>(c), H, W, OH, c.u_lo, c.u_base);
+  count_launch();
+  if (c.u_lo > 0) {
+    lanczos_v_kernel<<<dim3((W + 255) / 256, c.u_lo, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OH, 0);
+    count_launch();
+  }
+  if (done_hi < OH) {
+    lanczos_v_kernel<<<dim3((W + 255) / 256, OH - done_hi, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OH, done_hi);
+    count_launch();
+  }
+  return true;
+}
+
+static bool uniform_h(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk, int C,
+                      int H, int W, int OW, cudaStream_t st) {
+  if (c.u_step == 2 && c.u_taps == 12) return uniform_h_launch<2, 12, 8>(c, in, out, db, dk, C, H, W, OW, st);
+  if (c.u_step == 3 && c.u_taps == 18) return uniform_h_launch<3, 18, 4>(c, in, out, db, dk, C, H, W, OW, st);
+  if (c.u_step == 4 && c.u_taps == 24) return uniform_h_launch<4, 24, 4>(c, in, out, db, dk, C, H, W, OW, st);
+  return false;
+}
+static bool uniform_v(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk, int C,
+                      int H, int W, int OH, cudaStream_t st) {
+  if (c.u_step == 2 && c.u_taps == 12) return uniform_v_launch<2, 12, 8>(c, in, out, db, dk, C, H, W, OH, st);
+  if (c.u_step == 3 && c.u_taps == 18) return uniform_v_launch<3, 18, 4>(c, in, out, db, dk, C, H, W, OH, st);
+  if (c.u_step == 4 && c.u_taps == 24) return uniform_v_launch<4, 24, 4>(c, in, out, db, dk, C, H, W, OH, st);
+  return false;
 }
 
 }  // namespace ips
@@ -288,13 +468,15 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
     uint16_t* h_out = need_v ? tmp : out;
     const int span_max = lanczos_span_max(c, outW, LZ_TX);
     const size_t smem = ((size_t)LZ_RH * span_max + (size_t)LZ_TX * c.ksize) * sizeof(double);
-    if (smem <= LZ_SMEM_LIMIT && span_max <= LZ_SPAN_ITERS * LZ_TX && (H + LZ_RH - 1) / LZ_RH <= 65535) {
+    if (uniform_h(c, in, h_out, db, dk, C, H, W, outW, st)) {
+      // integer decimation: register kernel for the interior, the simple kernel for the edge columns
+    } else if (smem <= LZ_SMEM_LIMIT && span_max <= LZ_SPAN_ITERS * LZ_TX && (H + LZ_RH - 1) / LZ_RH <= 65535) {
       IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_h_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       lanczos_h_staged_kernel<<<dim3((outW + LZ_TX - 1) / LZ_TX, (H + LZ_RH - 1) / LZ_RH, C), LZ_TX, smem, st>>>(
           in, h_out, db, dk, c.ksize, H, W, outW, span_max);
       IPS_LAUNCH_OK("lanczos_h_staged_kernel");
     } else {
-      lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW);
+      lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW, 0, outW);
       IPS_LAUNCH_OK("lanczos_h_kernel");
     }
     v_in = h_out;
@@ -308,13 +490,15 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
     IPS_CUDA_OK(cudaMemcpyAsync(dk, c.kk.data(), c.kk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     const int span_max = lanczos_span_max(c, outH, LZ_RV);
     const size_t smem = ((size_t)span_max * LZ_TX + (size_t)LZ_RV * c.ksize) * sizeof(double);
-    if (smem <= LZ_SMEM_LIMIT) {
+    if (uniform_v(c, v_in, out, db, dk, C, H, v_W, outH, st)) {
+      // integer decimation: register kernel for the interior, the simple kernel for the edge rows
+    } else if (smem <= LZ_SMEM_LIMIT) {
       IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_v_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       lanczos_v_staged_kernel<<<dim3((v_W + LZ_TX - 1) / LZ_TX, (outH + LZ_RV - 1) / LZ_RV, C), LZ_TX, smem, st>>>(
           v_in, out, db, dk, c.ksize, H, v_W, outH, span_max);
       IPS_LAUNCH_OK("lanczos_v_staged_kernel");
     } else {
-      lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH);
+      lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH, 0);
       IPS_LAUNCH_OK("lanczos_v_kernel");
     }
   }

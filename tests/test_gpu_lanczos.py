@@ -21,7 +21,8 @@ def test_lanczos_golden(golden_dir, case):
     np.testing.assert_array_equal(got, ref)
 
 
-@pytest.mark.parametrize("shape,out", [((2, 216, 216), (108, 108)), ((1, 216, 216), (54, 54)),
+@pytest.mark.parametrize("shape,out", [((2, 216, 216), (108, 108)), ((1, 216, 216), (54, 54)), ((2, 216, 432), (72, 144)), ((1, 215, 431), (215, 431 // 1)),
+                                       ((2, 300, 201), (150, 67)), ((1, 256, 256), (64, 128)),
                                        ((3, 100, 150), (37, 61)), ((1, 64, 64), (64, 32)),
                                        ((1, 64, 64), (32, 64)), ((1, 40, 40), (40, 40)),
                                        ((1, 30, 30), (75, 45))])
