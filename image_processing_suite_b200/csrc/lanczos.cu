@@ -332,6 +332,38 @@ lanczos_v_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__
   }
 }
 
+// the few outputs outside the uniform interior (clipped windows at the image border, and the
+// remainder of the last group): their windows and weights travel as kernel parameters, so the
+// integer-decimation path needs no coefficient upload at all
+constexpr int LZ_EDGE_MAX = 16, LZ_EDGE_TAPS = 25;
+struct LzEdges {
+  int count;
+  int index[LZ_EDGE_MAX], first[LZ_EDGE_MAX], taps[LZ_EDGE_MAX];
+  double w[LZ_EDGE_MAX][LZ_EDGE_TAPS];
+};
+
+__global__ void __launch_bounds__(256)
+lanczos_h_edge_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzEdges e, int H, int W, int OW) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y, p = blockIdx.z;
+  if (y >= H) return;
+  const uint16_t* row = in + ((size_t)p * H + y) * W + e.first[k];
+  double ss = 0.0;
+  for (int t = 0; t < e.taps[k]; ++t) ss = __dadd_rn(ss, __dmul_rn((double)row[t], e.w[k][t]));
+  out[((size_t)p * H + y) * OW + e.index[k]] = pil_store_u16(ss);
+}
+
+__global__ void __launch_bounds__(256)
+lanczos_v_edge_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzEdges e, int H, int W, int OH) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y, p = blockIdx.z;
+  if (x >= W) return;
+  const uint16_t* col = in + ((size_t)p * H + e.first[k]) * W + x;
+  double ss = 0.0;
+  for (int t = 0; t < e.taps[k]; ++t) ss = __dadd_rn(ss, __dmul_rn((double)col[(size_t)t * W], e.w[k][t]));
+  out[((size_t)p * OH + e.index[k]) * W + x] = pil_store_u16(ss);
+}
+
 // largest input span any block of `per_block` consecutive outputs needs
 static int lanczos_span_max(const LanczosCoeffs& c, int n_out, int per_block) {
   int m = 1;
@@ -372,60 +404,71 @@ static LzWeights<STEP, TAPS> uniform_weights(const LanczosCoeffs& c) {
   return w;
 }
 
-// interior outputs through the register kernel, edges through the simple kernel; false = not applicable
+// outputs [0, lo) and [hi, n_out) as kernel parameters; false when they do not fit
+static bool make_edges(const LanczosCoeffs& c, int lo, int hi, int n_out, LzEdges* e) {
+  e->count = 0;
+  for (int o = 0; o < n_out; ++o) {
+    if (o >= lo && o < hi) {
+      o = hi - 1;
+      continue;
+    }
+    const int n = c.bounds[(size_t)o * 2 + 1];
+    if (e->count == LZ_EDGE_MAX || n > LZ_EDGE_TAPS) return false;
+    e->index[e->count] = o;
+    e->first[e->count] = c.bounds[(size_t)o * 2];
+    e->taps[e->count] = n;
+    for (int t = 0; t < n; ++t) e->w[e->count][t] = c.kk[(size_t)o * c.ksize + t];
+    e->count++;
+  }
+  return true;
+}
+
+// interior outputs through the register kernel, the rest through the edge kernel; false = not applicable
 template <int STEP, int TAPS, int NO>
-static bool uniform_h_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk,
-                             int C, int H, int W, int OW, cudaStream_t st) {
+static bool uniform_h_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, int C, int H, int W, int OW,
+                             cudaStream_t st) {
   const int groups = (c.u_hi - c.u_lo) / NO;
-  if (groups <= 0 || H > 65535) return false;
-  const int done_hi = c.u_lo + groups * NO;
+  LzEdges e;
+  if (groups <= 0 || H > 65535 || !make_edges(c, c.u_lo, c.u_lo + groups * NO, OW, &e)) return false;
   lanczos_h_uniform_kernel<STEP, TAPS, NO><<<dim3((groups + 127) / 128, H, C), 128, 0, st>>>(
       in, out, uniform_weights<STEP, TAPS>(c), H, W, OW, c.u_lo, c.u_base, groups);
   count_launch();
-  if (c.u_lo > 0) {
-    lanczos_h_kernel<<<dim3((c.u_lo + 255) / 256, H, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OW, 0, c.u_lo);
-    count_launch();
-  }
-  if (done_hi < OW) {
-    lanczos_h_kernel<<<dim3((OW - done_hi + 255) / 256, H, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OW, done_hi, OW);
+  if (e.count) {
+    lanczos_h_edge_kernel<<<dim3((H + 255) / 256, e.count, C), 256, 0, st>>>(in, out, e, H, W, OW);
     count_launch();
   }
   return true;
 }
 
 template <int STEP, int TAPS, int NO>
-static bool uniform_v_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk,
-                             int C, int H, int W, int OH, cudaStream_t st) {
+static bool uniform_v_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, int C, int H, int W, int OH,
+                             cudaStream_t st) {
   const int groups = (c.u_hi - c.u_lo) / NO;
-  if (groups <= 0 || groups > 65535) return false;
-  const int done_hi = c.u_lo + groups * NO;
+  LzEdges e;
+  if (groups <= 0 || groups > 65535 || !make_edges(c, c.u_lo, c.u_lo + groups * NO, OH, &e)) return false;
   const int pairs = (W + 1) / 2;
   lanczos_v_uniform_kernel<STEP, TAPS, NO><<<dim3((pairs + 127) / 128, groups, C), 128, 0, st>>>(
       in, out, uniform_weights<STEP, TAPS>(c), H, W, OH, c.u_lo, c.u_base);
   count_launch();
-  if (c.u_lo > 0) {
-    lanczos_v_kernel<<<dim3((W + 255) / 256, c.u_lo, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OH, 0);
-    count_launch();
-  }
-  if (done_hi < OH) {
-    lanczos_v_kernel<<<dim3((W + 255) / 256, OH - done_hi, C), 256, 0, st>>>(in, out, db, dk, c.ksize, H, W, OH, done_hi);
+  if (e.count) {
+    lanczos_v_edge_kernel<<<dim3((W + 255) / 256, e.count, C), 256, 0, st>>>(in, out, e, H, W, OH);
     count_launch();
   }
   return true;
 }
 
-static bool uniform_h(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk, int C,
-                      int H, int W, int OW, cudaStream_t st) {
-  if (c.u_step == 2 && c.u_taps == 12) return uniform_h_launch<2, 12, 8>(c, in, out, db, dk, C, H, W, OW, st);
-  if (c.u_step == 3 && c.u_taps == 18) return uniform_h_launch<3, 18, 4>(c, in, out, db, dk, C, H, W, OW, st);
-  if (c.u_step == 4 && c.u_taps == 24) return uniform_h_launch<4, 24, 4>(c, in, out, db, dk, C, H, W, OW, st);
+static bool uniform_h(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, int C, int H, int W, int OW,
+                      cudaStream_t st) {
+  if (c.u_step == 2 && c.u_taps == 12) return uniform_h_launch<2, 12, 8>(c, in, out, C, H, W, OW, st);
+  if (c.u_step == 3 && c.u_taps == 18) return uniform_h_launch<3, 18, 4>(c, in, out, C, H, W, OW, st);
+  if (c.u_step == 4 && c.u_taps == 24) return uniform_h_launch<4, 24, 4>(c, in, out, C, H, W, OW, st);
   return false;
 }
-static bool uniform_v(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, const int* db, const double* dk, int C,
-                      int H, int W, int OH, cudaStream_t st) {
-  if (c.u_step == 2 && c.u_taps == 12) return uniform_v_launch<2, 12, 8>(c, in, out, db, dk, C, H, W, OH, st);
-  if (c.u_step == 3 && c.u_taps == 18) return uniform_v_launch<3, 18, 4>(c, in, out, db, dk, C, H, W, OH, st);
-  if (c.u_step == 4 && c.u_taps == 24) return uniform_v_launch<4, 24, 4>(c, in, out, db, dk, C, H, W, OH, st);
+static bool uniform_v(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, int C, int H, int W, int OH,
+                      cudaStream_t st) {
+  if (c.u_step == 2 && c.u_taps == 12) return uniform_v_launch<2, 12, 8>(c, in, out, C, H, W, OH, st);
+  if (c.u_step == 3 && c.u_taps == 18) return uniform_v_launch<3, 18, 4>(c, in, out, C, H, W, OH, st);
+  if (c.u_step == 4 && c.u_taps == 24) return uniform_v_launch<4, 24, 4>(c, in, out, C, H, W, OH, st);
   return false;
 }
 
@@ -461,46 +504,48 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
   int v_W = W;
   if (need_h) {
     const LanczosCoeffs& c = cached_coeffs(W, outW);
-    int* db = reinterpret_cast<int*>(base + L.hb);
-    double* dk = reinterpret_cast<double*>(base + L.hk);
-    IPS_CUDA_OK(cudaMemcpyAsync(db, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    IPS_CUDA_OK(cudaMemcpyAsync(dk, c.kk.data(), c.kk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     uint16_t* h_out = need_v ? tmp : out;
-    const int span_max = lanczos_span_max(c, outW, LZ_TX);
-    const size_t smem = ((size_t)LZ_RH * span_max + (size_t)LZ_TX * c.ksize) * sizeof(double);
-    if (uniform_h(c, in, h_out, db, dk, C, H, W, outW, st)) {
-      // integer decimation: register kernel for the interior, the simple kernel for the edge columns
-    } else if (smem <= LZ_SMEM_LIMIT && span_max <= LZ_SPAN_ITERS * LZ_TX && (H + LZ_RH - 1) / LZ_RH <= 65535) {
-      IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_h_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      lanczos_h_staged_kernel<<<dim3((outW + LZ_TX - 1) / LZ_TX, (H + LZ_RH - 1) / LZ_RH, C), LZ_TX, smem, st>>>(
-          in, h_out, db, dk, c.ksize, H, W, outW, span_max);
-      IPS_LAUNCH_OK("lanczos_h_staged_kernel");
-    } else {
-      lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW, 0, outW);
-      IPS_LAUNCH_OK("lanczos_h_kernel");
+    if (!uniform_h(c, in, h_out, C, H, W, outW, st)) {     // integer decimation needs no tables on the device
+      int* db = reinterpret_cast<int*>(base + L.hb);
+      double* dk = reinterpret_cast<double*>(base + L.hk);
+      IPS_CUDA_OK(cudaMemcpyAsync(db, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      IPS_CUDA_OK(cudaMemcpyAsync(dk, c.kk.data(), c.kk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      const int span_max = lanczos_span_max(c, outW, LZ_TX);
+      const size_t smem = ((size_t)LZ_RH * span_max + (size_t)LZ_TX * c.ksize) * sizeof(double);
+      if (smem <= LZ_SMEM_LIMIT && span_max <= LZ_SPAN_ITERS * LZ_TX && (H + LZ_RH - 1) / LZ_RH <= 65535) {
+        IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_h_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lanczos_h_staged_kernel<<<dim3((outW + LZ_TX - 1) / LZ_TX, (H + LZ_RH - 1) / LZ_RH, C), LZ_TX, smem, st>>>(
+            in, h_out, db, dk, c.ksize, H, W, outW, span_max);
+        IPS_LAUNCH_OK("lanczos_h_staged_kernel");
+      } else {
+        lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW, 0, outW);
+        IPS_LAUNCH_OK("lanczos_h_kernel");
+      }
     }
+    IPS_CUDA_OK(cudaGetLastError());
     v_in = h_out;
     v_W = outW;
   }
   if (need_v) {
     const LanczosCoeffs& c = cached_coeffs(H, outH);
-    int* db = reinterpret_cast<int*>(base + L.vb);
-    double* dk = reinterpret_cast<double*>(base + L.vk);
-    IPS_CUDA_OK(cudaMemcpyAsync(db, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    IPS_CUDA_OK(cudaMemcpyAsync(dk, c.kk.data(), c.kk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    const int span_max = lanczos_span_max(c, outH, LZ_RV);
-    const size_t smem = ((size_t)span_max * LZ_TX + (size_t)LZ_RV * c.ksize) * sizeof(double);
-    if (uniform_v(c, v_in, out, db, dk, C, H, v_W, outH, st)) {
-      // integer decimation: register kernel for the interior, the simple kernel for the edge rows
-    } else if (smem <= LZ_SMEM_LIMIT) {
-      IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_v_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      lanczos_v_staged_kernel<<<dim3((v_W + LZ_TX - 1) / LZ_TX, (outH + LZ_RV - 1) / LZ_RV, C), LZ_TX, smem, st>>>(
-          v_in, out, db, dk, c.ksize, H, v_W, outH, span_max);
-      IPS_LAUNCH_OK("lanczos_v_staged_kernel");
-    } else {
-      lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH, 0);
-      IPS_LAUNCH_OK("lanczos_v_kernel");
+    if (!uniform_v(c, v_in, out, C, H, v_W, outH, st)) {
+      int* db = reinterpret_cast<int*>(base + L.vb);
+      double* dk = reinterpret_cast<double*>(base + L.vk);
+      IPS_CUDA_OK(cudaMemcpyAsync(db, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      IPS_CUDA_OK(cudaMemcpyAsync(dk, c.kk.data(), c.kk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      const int span_max = lanczos_span_max(c, outH, LZ_RV);
+      const size_t smem = ((size_t)span_max * LZ_TX + (size_t)LZ_RV * c.ksize) * sizeof(double);
+      if (smem <= LZ_SMEM_LIMIT) {
+        IPS_CUDA_OK(cudaFuncSetAttribute(lanczos_v_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lanczos_v_staged_kernel<<<dim3((v_W + LZ_TX - 1) / LZ_TX, (outH + LZ_RV - 1) / LZ_RV, C), LZ_TX, smem, st>>>(
+            v_in, out, db, dk, c.ksize, H, v_W, outH, span_max);
+        IPS_LAUNCH_OK("lanczos_v_staged_kernel");
+      } else {
+        lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH, 0);
+        IPS_LAUNCH_OK("lanczos_v_kernel");
+      }
     }
+    IPS_CUDA_OK(cudaGetLastError());
   }
   return IPS_OK;
 }
