@@ -111,8 +111,9 @@ static const LanczosCoeffs& cached_coeffs(int in_size, int out_size) {
   return it->second;
 }
 
+// |ss| <= 65535 * sum|w| < 2^18: the conversion never leaves int32
 __device__ __forceinline__ uint16_t pil_store_u16(double ss) {
-  const long long v = __double2ll_rz(ss >= 0.0 ? ss + 0.5 : ss - 0.5);
+  const int v = __double2int_rz(ss >= 0.0 ? ss + 0.5 : ss - 0.5);
   if (v < 0) return 0;
   if (v > 65535) return (uint16_t)(0xFF00u | (unsigned)(v & 0xFF));
   return (uint16_t)v;
@@ -260,44 +261,90 @@ struct LzWeights {
   double w[TAPS];
 };
 
-// rows: thread = NO consecutive outputs of one row; lanes side by side along the row
+// the few outputs outside the uniform interior (clipped windows at the image border, and the
+// remainder of the last group): their windows and weights travel as kernel parameters and spare
+// threads / block rows of the same launch compute them, so the integer-decimation path needs no
+// coefficient upload and no extra launch
+constexpr int LZ_EDGE_MAX = 16, LZ_EDGE_TAPS = 25;
+struct LzEdges {
+  int count;
+  int index[LZ_EDGE_MAX], first[LZ_EDGE_MAX], taps[LZ_EDGE_MAX];
+  double w[LZ_EDGE_MAX][LZ_EDGE_TAPS];
+};
+
+// rows: thread = NO consecutive outputs of one row, lanes side by side along the row.  The block's
+// input span is read once with coalesced loads, converted once and parked in shared memory (one
+// pad per thread chunk: conflict-free); threads behind the last group take the edge outputs.
 template <int STEP, int TAPS, int NO>
 __global__ void __launch_bounds__(128)
-lanczos_h_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzWeights<STEP, TAPS> wt, int H,
-                         int W, int OW, int u_lo, int u_base, int groups) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+lanczos_h_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, const LzWeights<STEP, TAPS> wt,
+                         const LzEdges e, int H, int W, int OW, int u_lo, int u_base, int groups) {
+  constexpr int CH = NO * STEP;                       // inputs a thread advances by
+  constexpr int NIN = CH + TAPS - STEP;               // inputs a thread reads
+  constexpr int SPAN = 128 * CH + TAPS - STEP;        // inputs a block reads
+  __shared__ double px_s[SPAN + SPAN / CH + 1];
+  const int g0 = blockIdx.x * 128;
   const int y = blockIdx.y, p = blockIdx.z;
-  if (g >= groups) return;
-  const int o0 = u_lo + g * NO;
-  const uint16_t* src = in + ((size_t)p * H + y) * W + u_base + STEP * o0;
-  constexpr int NIN = NO * STEP + TAPS - STEP;
-  double ss[NO];
-#pragma unroll
-  for (int o = 0; o < NO; ++o) ss[o] = 0.0;
-#pragma unroll
-  for (int i = 0; i < NIN; ++i) {
-    const double px = (double)src[i];
-#pragma unroll
-    for (int o = 0; o < NO; ++o) {
-      const int t = i - STEP * o;
-      if (t >= 0 && t < TAPS) ss[o] = __dadd_rn(ss[o], __dmul_rn(px, wt.w[t]));
-    }
+  const uint16_t* row = in + ((size_t)p * H + y) * W;
+  uint16_t* orow = out + ((size_t)p * H + y) * OW;
+  const int here = min(128, groups - g0);             // groups of this block (<= 0: edge-only block)
+  if (here > 0) {
+    const uint16_t* src = row + u_base + STEP * (u_lo + g0 * NO);
+    const int span = here * CH + TAPS - STEP;
+    for (int i = threadIdx.x; i < span; i += 128) px_s[i + i / CH] = (double)src[i];
   }
-  uint16_t* dst = out + ((size_t)p * H + y) * OW + o0;
+  __syncthreads();
+  const int g = g0 + threadIdx.x;
+  if (g < groups) {
+    double ss[NO];
 #pragma unroll
-  for (int o = 0; o < NO; ++o) dst[o] = pil_store_u16(ss[o]);
+    for (int o = 0; o < NO; ++o) ss[o] = 0.0;
+    const double* mine = px_s + threadIdx.x * (CH + 1);
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) {
+      const double px = mine[i + i / CH];
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const int t = i - STEP * o;
+        if (t >= 0 && t < TAPS) ss[o] = __dadd_rn(ss[o], __dmul_rn(px, wt.w[t]));
+      }
+    }
+    uint16_t* dst = orow + u_lo + g * NO;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) dst[o] = pil_store_u16(ss[o]);
+  } else if (g - groups < e.count) {
+    const int k = g - groups;
+    const uint16_t* src = row + e.first[k];
+    double ss = 0.0;
+    for (int t = 0; t < e.taps[k]; ++t) ss = __dadd_rn(ss, __dmul_rn((double)src[t], e.w[k][t]));
+    orow[e.index[k]] = pil_store_u16(ss);
+  }
 }
 
-// columns: thread = NO consecutive output rows of two adjacent columns; lanes side by side along the row
-template <int STEP, int TAPS, int NO>
+// columns: thread = NO consecutive output rows of two adjacent columns, lanes side by side along
+// the row (coalesced); block rows behind the last group take the edge rows
+template <int STEP, int TAPS, int NO, bool PAIRED>
 __global__ void __launch_bounds__(128)
-lanczos_v_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzWeights<STEP, TAPS> wt, int H,
-                         int W, int OH, int u_lo, int u_base) {
+lanczos_v_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, const LzWeights<STEP, TAPS> wt,
+                         const LzEdges e, int H, int W, int OH, int u_lo, int u_base, int groups) {
   const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int p = blockIdx.z;
   if (x >= W) return;
-  const int o0 = u_lo + blockIdx.y * NO;
   const bool pair = x + 1 < W;
+  if ((int)blockIdx.y >= groups) {                     // an edge row
+    const int k = blockIdx.y - groups;
+    const uint16_t* col = in + ((size_t)p * H + e.first[k]) * W + x;
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < e.taps[k]; ++t) {
+      a = __dadd_rn(a, __dmul_rn((double)col[(size_t)t * W], e.w[k][t]));
+      if (pair) b = __dadd_rn(b, __dmul_rn((double)col[(size_t)t * W + 1], e.w[k][t]));
+    }
+    uint16_t* dst = out + ((size_t)p * OH + e.index[k]) * W + x;
+    dst[0] = pil_store_u16(a);
+    if (pair) dst[1] = pil_store_u16(b);
+    return;
+  }
+  const int o0 = u_lo + blockIdx.y * NO;
   const uint16_t* src = in + ((size_t)p * H + u_base + STEP * o0) * W + x;
   constexpr int NIN = NO * STEP + TAPS - STEP;
   double s0[NO], s1[NO];
@@ -307,7 +354,7 @@ lanczos_v_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__
   for (int i = 0; i < NIN; ++i) {
     const uint16_t* q = src + (size_t)i * W;
     double a, b = 0.0;
-    if (pair && ((reinterpret_cast<uintptr_t>(q) & 3u) == 0)) {
+    if (PAIRED) {                                      // W even and the planes 4-byte aligned: one load for both columns
       const uint32_t v = *reinterpret_cast<const uint32_t*>(q);
       a = (double)(v & 0xFFFFu);
       b = (double)(v >> 16);
@@ -324,44 +371,16 @@ lanczos_v_uniform_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__
       }
     }
   }
+  uint16_t* dst = out + ((size_t)p * OH + o0) * W + x;
 #pragma unroll
   for (int o = 0; o < NO; ++o) {
-    uint16_t* dst = out + ((size_t)p * OH + o0 + o) * W + x;
-    dst[0] = pil_store_u16(s0[o]);
-    if (pair) dst[1] = pil_store_u16(s1[o]);
+    if (PAIRED) {
+      *reinterpret_cast<uint32_t*>(dst + (size_t)o * W) = (uint32_t)pil_store_u16(s0[o]) | ((uint32_t)pil_store_u16(s1[o]) << 16);
+    } else {
+      dst[(size_t)o * W] = pil_store_u16(s0[o]);
+      if (pair) dst[(size_t)o * W + 1] = pil_store_u16(s1[o]);
+    }
   }
-}
-
-// the few outputs outside the uniform interior (clipped windows at the image border, and the
-// remainder of the last group): their windows and weights travel as kernel parameters, so the
-// integer-decimation path needs no coefficient upload at all
-constexpr int LZ_EDGE_MAX = 16, LZ_EDGE_TAPS = 25;
-struct LzEdges {
-  int count;
-  int index[LZ_EDGE_MAX], first[LZ_EDGE_MAX], taps[LZ_EDGE_MAX];
-  double w[LZ_EDGE_MAX][LZ_EDGE_TAPS];
-};
-
-__global__ void __launch_bounds__(256)
-lanczos_h_edge_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzEdges e, int H, int W, int OW) {
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = blockIdx.y, p = blockIdx.z;
-  if (y >= H) return;
-  const uint16_t* row = in + ((size_t)p * H + y) * W + e.first[k];
-  double ss = 0.0;
-  for (int t = 0; t < e.taps[k]; ++t) ss = __dadd_rn(ss, __dmul_rn((double)row[t], e.w[k][t]));
-  out[((size_t)p * H + y) * OW + e.index[k]] = pil_store_u16(ss);
-}
-
-__global__ void __launch_bounds__(256)
-lanczos_v_edge_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, LzEdges e, int H, int W, int OH) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = blockIdx.y, p = blockIdx.z;
-  if (x >= W) return;
-  const uint16_t* col = in + ((size_t)p * H + e.first[k]) * W + x;
-  double ss = 0.0;
-  for (int t = 0; t < e.taps[k]; ++t) ss = __dadd_rn(ss, __dmul_rn((double)col[(size_t)t * W], e.w[k][t]));
-  out[((size_t)p * OH + e.index[k]) * W + x] = pil_store_u16(ss);
 }
 
 // largest input span any block of `per_block` consecutive outputs needs
@@ -423,20 +442,16 @@ static bool make_edges(const LanczosCoeffs& c, int lo, int hi, int n_out, LzEdge
   return true;
 }
 
-// interior outputs through the register kernel, the rest through the edge kernel; false = not applicable
+// interior outputs and edge outputs in one launch; false = not applicable
 template <int STEP, int TAPS, int NO>
 static bool uniform_h_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_t* out, int C, int H, int W, int OW,
                              cudaStream_t st) {
   const int groups = (c.u_hi - c.u_lo) / NO;
   LzEdges e;
   if (groups <= 0 || H > 65535 || !make_edges(c, c.u_lo, c.u_lo + groups * NO, OW, &e)) return false;
-  lanczos_h_uniform_kernel<STEP, TAPS, NO><<<dim3((groups + 127) / 128, H, C), 128, 0, st>>>(
-      in, out, uniform_weights<STEP, TAPS>(c), H, W, OW, c.u_lo, c.u_base, groups);
+  lanczos_h_uniform_kernel<STEP, TAPS, NO><<<dim3((groups + e.count + 127) / 128, H, C), 128, 0, st>>>(
+      in, out, uniform_weights<STEP, TAPS>(c), e, H, W, OW, c.u_lo, c.u_base, groups);
   count_launch();
-  if (e.count) {
-    lanczos_h_edge_kernel<<<dim3((H + 255) / 256, e.count, C), 256, 0, st>>>(in, out, e, H, W, OW);
-    count_launch();
-  }
   return true;
 }
 
@@ -445,15 +460,17 @@ static bool uniform_v_launch(const LanczosCoeffs& c, const uint16_t* in, uint16_
                              cudaStream_t st) {
   const int groups = (c.u_hi - c.u_lo) / NO;
   LzEdges e;
-  if (groups <= 0 || groups > 65535 || !make_edges(c, c.u_lo, c.u_lo + groups * NO, OH, &e)) return false;
+  if (groups <= 0 || groups + LZ_EDGE_MAX > 65535 || !make_edges(c, c.u_lo, c.u_lo + groups * NO, OH, &e)) return false;
   const int pairs = (W + 1) / 2;
-  lanczos_v_uniform_kernel<STEP, TAPS, NO><<<dim3((pairs + 127) / 128, groups, C), 128, 0, st>>>(
-      in, out, uniform_weights<STEP, TAPS>(c), H, W, OH, c.u_lo, c.u_base);
+  const dim3 grid((pairs + 127) / 128, groups + e.count, C);
+  const bool paired = W % 2 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3u) == 0;
+  if (paired)
+    lanczos_v_uniform_kernel<STEP, TAPS, NO, true><<<grid, 128, 0, st>>>(in, out, uniform_weights<STEP, TAPS>(c), e, H, W, OH,
+                                                                        c.u_lo, c.u_base, groups);
+  else
+    lanczos_v_uniform_kernel<STEP, TAPS, NO, false><<<grid, 128, 0, st>>>(in, out, uniform_weights<STEP, TAPS>(c), e, H, W, OH,
+                                                                         c.u_lo, c.u_base, groups);
   count_launch();
-  if (e.count) {
-    lanczos_v_edge_kernel<<<dim3((W + 255) / 256, e.count, C), 256, 0, st>>>(in, out, e, H, W, OH);
-    count_launch();
-  }
   return true;
 }
 
