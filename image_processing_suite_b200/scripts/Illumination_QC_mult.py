@@ -105,23 +105,48 @@ def calculate_qc_metrics(image, channel_name):
     return results
 
 
+_illum_dev = {}
+_illum_lock = threading.Lock()
+
+
+def _illum_on_device(illum):
+    """(float64 tensor, float32 tensor or None) of one illumination function, uploaded once per
+    array (the cache of load_illum_cache is shared by every site, Illumination_QC_mult.py:196-199).
+    The float32 copy exists only when the function is float32-exact, which is when the fused
+    kernel's divide-side PercentMaximal applies."""
+    import torch
+    illum = np.asarray(illum)
+    key = (illum.__array_interface__["data"][0], illum.shape, illum.strides, illum.dtype.str)
+    with _illum_lock:
+        hit = _illum_dev.get(key)
+        if hit is not None:
+            return hit[1], hit[2]
+    ill64 = np.ascontiguousarray(illum, dtype=np.float64)
+    ill32 = ill64.astype(np.float32)
+    d64 = torch.from_numpy(ill64).cuda()
+    d32 = torch.from_numpy(ill32[None]).cuda() if np.array_equal(ill32.astype(np.float64), ill64) else None
+    with _illum_lock:
+        if len(_illum_dev) > 64:
+            _illum_dev.clear()
+        _illum_dev[key] = (illum, d64, d32)          # keeps the memory alive, so the key stays unique
+    return d64, d32
+
+
 def _corrected_and_pct(img_u16, illum):
     """(float64 corrected image on the device, PercentMaximal).  When the illumination
     function is float32-exact the fused kernel computes the divide-side PercentMaximal."""
     import torch
     from .. import ops
     raw = img_u16 if isinstance(img_u16, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img_u16)).cuda()
-    if illum is None or img_u16.shape != illum.shape:        # silently uncorrected (:148-153)
+    if illum is None or tuple(img_u16.shape) != tuple(illum.shape):        # silently uncorrected (:148-153)
         r = ops.preprocess_fused(raw[None, None, None], None, bin=1, want_maxproj=False, want_binned=False,
                                  want_pct_maximal=True)
         return raw.to(torch.float64), float(r["pct_maximal"][0, 0].item())
-    ill64 = np.ascontiguousarray(illum, dtype=np.float64)
-    ill32 = ill64.astype(np.float32)
-    d64 = torch.from_numpy(ill64).cuda()
+    d64, d32 = _illum_on_device(illum)
     corrected = raw.to(torch.float64) / d64
-    if np.array_equal(ill32.astype(np.float64), ill64):
-        r = ops.preprocess_fused(raw[None, None, None], torch.from_numpy(ill32[None]).cuda(), bin=1,
-                                 want_maxproj=False, want_binned=False, want_pct_maximal=True)
+    if d32 is not None:
+        r = ops.preprocess_fused(raw[None, None, None], d32, bin=1, want_maxproj=False, want_binned=False,
+                                 want_pct_maximal=True)
         return corrected, float(r["pct_maximal"][0, 0].item())
     return corrected, calculate_saturation_cp_exact(corrected)
 
