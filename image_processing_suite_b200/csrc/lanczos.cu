@@ -123,10 +123,10 @@ __device__ __forceinline__ uint16_t pil_store_u16(double ss) {
 __global__ void __launch_bounds__(256)
 lanczos_h_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                  const int* __restrict__ bounds, const double* __restrict__ kk, int ksize, int H,
-                 int W, int OW, int x_begin, int x_end) {
-  const int xx = x_begin + blockIdx.x * blockDim.x + threadIdx.x;
+                 int W, int OW) {
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, p = blockIdx.z;
-  if (xx >= x_end) return;
+  if (xx >= OW) return;
   const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
   const double* k = kk + (size_t)xx * ksize;
   const uint16_t* row = in + ((size_t)p * H + y) * W + xmin;
@@ -139,9 +139,9 @@ lanczos_h_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
 __global__ void __launch_bounds__(256)
 lanczos_v_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                  const int* __restrict__ bounds, const double* __restrict__ kk, int ksize, int H,
-                 int W, int OH, int y_begin) {
+                 int W, int OH) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int yy = y_begin + blockIdx.y, p = blockIdx.z;
+  const int yy = blockIdx.y, p = blockIdx.z;
   if (x >= W) return;
   const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
   const double* k = kk + (size_t)yy * ksize;
@@ -535,7 +535,7 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
             in, h_out, db, dk, c.ksize, H, W, outW, span_max);
         IPS_LAUNCH_OK("lanczos_h_staged_kernel");
       } else {
-        lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW, 0, outW);
+        lanczos_h_kernel<<<dim3((outW + 255) / 256, H, C), 256, 0, st>>>(in, h_out, db, dk, c.ksize, H, W, outW);
         IPS_LAUNCH_OK("lanczos_h_kernel");
       }
     }
@@ -558,7 +558,7 @@ extern "C" int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, 
             v_in, out, db, dk, c.ksize, H, v_W, outH, span_max);
         IPS_LAUNCH_OK("lanczos_v_staged_kernel");
       } else {
-        lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH, 0);
+        lanczos_v_kernel<<<dim3((v_W + 255) / 256, outH, C), 256, 0, st>>>(v_in, out, db, dk, c.ksize, H, v_W, outH);
         IPS_LAUNCH_OK("lanczos_v_kernel");
       }
     }
