@@ -116,7 +116,20 @@ def _dec(h, comp, n, off=0, ooff=0):
     return st, out[ooff:ooff + n].tobytes()
 
 
-@pytest.mark.parametrize("name,img", list(images()), ids=[n for n, _ in images()])
+def harness_images():
+    """Smaller than images(): 32 threads meeting at a barrier per warp collective are slow."""
+    rng = np.random.default_rng(15)
+    yield "noise", np.clip(rng.normal(300, 30, (24, 200)), 0, 65535).astype(np.uint16)
+    yield "zeros", np.zeros((70, 500), np.uint16)               # two strips; ratio check resets the table early
+    yield "const", np.full((64, 64), 65535, np.uint16)
+    yield "full", rng.integers(0, 65536, (40, 333)).astype(np.uint16)    # table fills: reset at code 4094
+    yield "ramp", (np.arange(100 * 300) % 1000).reshape(100, 300).astype(np.uint16)
+    yield "one", np.array([[7]], np.uint16)
+    yield "tall", rng.integers(0, 50, (900, 3)).astype(np.uint16)
+    yield "wide", rng.integers(0, 5, (2, 33000)).astype(np.uint16)      # stride > 64 KiB: one row per strip
+
+
+@pytest.mark.parametrize("name,img", list(harness_images()), ids=[n for n, _ in harness_images()])
 def test_kernel_state_machines_equal_pillow(harness, name, img):
     """Every strip Pillow writes: the kernels' encoder reproduces its bytes and the kernels'
     decoder its pixels, at every input / output alignment."""
@@ -125,7 +138,7 @@ def test_kernel_state_machines_equal_pillow(harness, name, img):
     rps = info["rps"]
     for s, (o, c) in enumerate(zip(info["offsets"], info["counts"])):
         raw = img[s * rps:(s + 1) * rps].tobytes()
-        for off in (range(4) if s == 0 else (s % 4,)):       # every alignment on the first strip, one on the others
+        for off in ((0, 1, 2, 3) if s == 0 and len(raw) < 12000 else ((s + 1) % 4, (s + 3) % 4)):   # every alignment on small first strips
             assert _enc(harness, raw, off) == ref[o:o + c]
             st, px = _dec(harness, ref[o:o + c], len(raw), off, (5 * off + s) % 16)
             assert st == 0 and px == raw
@@ -194,13 +207,13 @@ def _fuzz_strip(rng, kind, n):
     return rng.integers(0, 256, n, dtype=np.uint8)   # incompressible
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(10))
 def test_kernel_state_machines_fuzz(harness, seed):
     """Random strips of five entropy classes and odd lengths: the kernels' encoder equals the
     oracle's libtiff restatement, the kernels' decoder returns the bytes, truncated requests too."""
     rng = np.random.default_rng(1000 + seed)
     kind = seed % 5
-    n = int(rng.integers(1, 70000))
+    n = int(rng.integers(1, 40000))
     raw = np.ascontiguousarray(_fuzz_strip(rng, kind, n)).tobytes()
     off = int(rng.integers(0, 4))
     comp = _enc(harness, raw, off)
