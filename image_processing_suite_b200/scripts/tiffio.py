@@ -170,11 +170,13 @@ def load_planes(files, device=None):
     """list of encoded 16-bit images -> uint16 CUDA tensor [P][H][W]: the device codec when every
     file is a TIFF it reads, otherwise decode() on the host and one copy.  ValueError when the
     planes differ in shape or are not 16-bit."""
+    import logging
     import torch
     try:
         return decode_to_device(files, device)
-    except Unsupported:
-        pass
+    except Unsupported as why:
+        # not a silent switch: the reference decodes these with PIL too (PNG / JPEG / tiled or deflate TIFFs)
+        logging.getLogger(__name__).info("host image decoder used (%s); the arithmetic still runs on the GPU", why)
     images = [decode(f) for f in files]
     if not all(img.shape == images[0].shape for img in images):
         raise ValueError("Image shape mismatch")

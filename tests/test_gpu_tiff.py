@@ -230,3 +230,39 @@ def test_codec_fuzz_against_pillow(shape):
     np.testing.assert_array_equal(host(tiffio.decode_to_device(refs)), a)
     pred = [pil_file(a[p], compression="tiff_lzw", tiffinfo={317: 2}) for p in range(P)]
     np.testing.assert_array_equal(host(tiffio.decode_to_device(pred)), a)
+
+
+def test_entry_points_reject_bad_arguments():
+    """Error behaviour of the C ABI: status codes, nothing written."""
+    require_gpu()
+    import ctypes as C
+    import torch
+    from image_processing_suite_b200 import capi
+    H, W, rps = 64, 80, 7
+    planes = torch.zeros((2, H, W), dtype=torch.uint16, device="cuda")
+    cap = int(capi.call("ips_tiff_file_bound", H, W, rps))
+    files = torch.empty((2, cap), dtype=torch.uint8, device="cuda")
+    nbytes = torch.zeros((2,), dtype=torch.int64, device="cuda")
+    ws = torch.empty((int(capi.call("ips_tiff_encode_workspace_bytes", 2, H, W, rps)),), dtype=torch.uint8, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def code(*args):
+        with pytest.raises(capi.IpsError) as e:
+            capi.call("ips_tiff_lzw_encode_u16", *args)
+        return e.value.code
+
+    assert code(p(planes), 2, H, W, 0, p(files), cap, p(nbytes), p(ws), ws.numel(), st) == -1        # rows_per_strip
+    assert code(p(planes), 2, H, W, rps, p(files), cap - 16, p(nbytes), p(ws), ws.numel(), st) == -6  # file_cap below the bound
+    assert code(p(planes), 2, H, W, rps, p(files), cap, p(nbytes), p(ws), 16, st) == -6               # workspace
+    assert code(p(planes), 2, H, W, rps, C.c_void_p(files.data_ptr() + 1), cap, p(nbytes), p(ws), ws.numel(), st) == -3
+    assert code(C.c_void_p(0), 2, H, W, rps, p(files), cap, p(nbytes), p(ws), ws.numel(), st) == -7
+    assert capi.call("ips_tiff_lzw_encode_u16", p(planes), 0, H, W, rps, p(files), cap, p(nbytes), p(ws), ws.numel(), st) == 0
+    with pytest.raises(capi.IpsError) as e:
+        capi.call("ips_tiff_fix_u16", p(planes), 2 * H, W, 3, 0, st)
+    assert e.value.code == -7
+    with pytest.raises(capi.IpsError) as e:
+        capi.call("ips_tiff_lzw_decode", p(files), C.c_void_p(0), C.c_void_p(0), p(files), C.c_void_p(0), C.c_void_p(0), 1, C.c_void_p(0), st)
+    assert e.value.code == -7
+    assert int(capi.call("ips_tiff_rows_per_strip", 2160, 2160)) == 15 and int(capi.call("ips_tiff_rows_per_strip", 2, 40000)) == 1
+    assert int(capi.call("ips_tiff_lzw_bound", 64800)) >= 64800 * 3 // 2
