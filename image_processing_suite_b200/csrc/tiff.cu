@@ -247,7 +247,7 @@ extern "C" int ips_tiff_lzw_encode_u16(const uint16_t* planes, int P, int H, int
   if (P == 0) return IPS_OK;
   if (!planes || !files || !file_bytes || !ws) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_tiff_lzw_encode_u16: null pointer");
   if (!aligned16(files) || !aligned16(ws) || (file_cap & 15)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_tiff_lzw_encode_u16: files, ws and file_cap must be 16-byte aligned");
-  if ((size_t)rows_per_strip * W * 2 >= (1ull << 31)) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_tiff_lzw_encode_u16: strip larger than 2 GiB");
+  if ((size_t)rows_per_strip * W * 2 >= (1ull << 28)) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_tiff_lzw_encode_u16: strips of 256 MiB or more are not supported");
   if (file_cap < ips_tiff_file_bound(H, W, rows_per_strip) || file_cap >= (1ull << 32))
     IPS_FAIL(IPS_ERR_NOMEM, "ips_tiff_lzw_encode_u16: file_cap %zu outside [ips_tiff_file_bound, 4 GiB)", file_cap);
   if (ws_bytes < ips_tiff_encode_workspace_bytes(P, H, W, rows_per_strip)) IPS_FAIL(IPS_ERR_NOMEM, "ips_tiff_lzw_encode_u16: workspace too small");

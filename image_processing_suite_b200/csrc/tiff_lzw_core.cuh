@@ -408,6 +408,7 @@ LZW_HD int decode_strip(const uint8_t* in, uint32_t n_in, uint8_t* out, uint32_t
   const uint32_t lane = (uint32_t)w.lane;
   int status = ST_OK;
   if (n_in >= 2 && in[0] == 0 && (in[1] & 1)) status = ST_OLD_STYLE;   // pre-6.0 LSB-first streams
+  if (n_in >= (1u << 29)) status = ST_CORRUPT;                          // bit positions are 32-bit
   BitReader br;
   br.begin(in, n_in);
   const uint32_t total_bits = n_in * 8u;

@@ -228,7 +228,8 @@ int ips_cell_crops(const float* corrected, const int32_t* labels, const int32_t*
  *                           fit; cannot happen with file_cap >= ips_tiff_file_bound).
  * ips_tiff_lzw_decode       n_strips LZW streams src[src_off[s] .. +src_bytes[s]) -> exactly
  *                           dst_bytes[s] bytes at dst[dst_off[s]]; status[s] = 0, or 1 truncated,
- *                           2 corrupt, 3 pre-6.0 bit order (the remainder is zero-filled).
+ *                           2 corrupt (or a stream of 512 MiB or more), 3 pre-6.0 bit order (the
+ *                           remainder is zero-filled).
  *                           The five descriptor arrays are device pointers.
  * ips_tiff_fix_u16          in place on rows x W samples: byte swap (big-endian files), then
  *                           running sum modulo 2^16 along the row when predictor == 2.
