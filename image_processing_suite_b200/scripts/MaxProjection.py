@@ -38,22 +38,30 @@ def _fetch(image_key, bucket_name, s3_client):
     return s3_client.get_object(Bucket=bucket_name, Key=image_key)['Body'].read()
 
 
-def _load_group(keys, bucket_name, s3_client):
+def _decode_group(blobs, keys):
     """Encoded planes of one channel -> uint16 CUDA tensor [Z][H][W] (TIFF strips decoded on the
     device); ValueError on a shape mismatch like MaxProjection.py:42-43."""
     try:
-        planes = tiffio.load_planes([_fetch(k, bucket_name, s3_client) for k in keys])
+        return tiffio.load_planes(blobs)
     except ValueError as e:
         if "shape mismatch" in str(e):
             raise ValueError(f"Image shape mismatch in group: {keys}")
         raise
-    return planes
+
+
+def _load_group(keys, bucket_name, s3_client):
+    return _decode_group([_fetch(k, bucket_name, s3_client) for k in keys], keys)
 
 
 def _project(stack_czhw):
-    """[C][Z][H][W] uint16 (device) -> [C][H][W] uint16 (host) via the CUDA kernel."""
+    """[C][Z][H][W] uint16 (device) -> [C][H][W] uint16 (host, through a page-locked buffer) via the CUDA kernel."""
+    import torch
     from .. import ops
-    return ops.preprocess_fused(stack_czhw[None].contiguous(), None, bin=1, want_binned=False)["maxproj"][0].cpu().numpy()
+    dev = ops.preprocess_fused(stack_czhw[None].contiguous(), None, bin=1, want_binned=False)["maxproj"][0]
+    host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+    host.copy_(dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
 
 
 def max_projection(image_group, bucket_name, s3_client):
@@ -68,13 +76,28 @@ def max_project_chunk(groups, bucket_name, s3_client):
     channels whose planes fail to load or mismatch are reported like the reference does
     (logged, the other channels still go through).  Returns the number written."""
     import torch
-    stacks, ok = [], []
+    blobs = {}
     for j, group in enumerate(groups):
         try:
-            stacks.append(_load_group(group, bucket_name, s3_client))
-            ok.append(j)
+            blobs[j] = [_fetch(k, bucket_name, s3_client) for k in group]
         except Exception as e:
             logger.error(f"Error processing group {j}: {e}")
+    stacks, ok = [], []
+    try:                                        # the whole field in one device decode
+        flat = tiffio.decode_to_device([b for j in sorted(blobs) for b in blobs[j]])
+        at = 0
+        for j in sorted(blobs):
+            stacks.append(flat[at:at + len(blobs[j])])
+            ok.append(j)
+            at += len(blobs[j])
+    except Exception:                           # mixed shapes, a damaged or foreign file: channel by channel
+        stacks, ok = [], []
+        for j in sorted(blobs):
+            try:
+                stacks.append(_decode_group(blobs[j], groups[j]))
+                ok.append(j)
+            except Exception as e:
+                logger.error(f"Error processing group {j}: {e}")
     written = 0
     by_shape = {}
     for j, st in zip(ok, stacks):

@@ -24,9 +24,25 @@ def read(path):
         return decode(f.read())
 
 
+def _encode_plain_u16(arr):
+    """Uncompressed little-endian baseline TIFF of a 2-D uint16 array: header, the pixels as one
+    strip, one IFD (what imageio.imwrite(..., format='tiff') amounts to, MaxProjection.py:48)."""
+    import struct
+    h, w = arr.shape
+    data = np.ascontiguousarray(arr, dtype="<u2")
+    nbytes = data.nbytes
+    pad = nbytes & 1
+    tags = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8),
+            (277, 3, 1, 1), (278, 4, 1, h), (279, 4, 1, nbytes)]
+    ifd = struct.pack("<H", len(tags)) + b"".join(struct.pack("<HHII", *t) for t in tags) + struct.pack("<I", 0)
+    return b"".join([b"II*\x00", struct.pack("<I", 8 + nbytes + pad), memoryview(data).cast("B"), b"\x00" * pad, ifd])
+
+
 def encode(arr, compression=None):
     """2-D uint16 / uint8 array -> TIFF bytes (compression None or 'tiff_lzw')."""
     arr = np.ascontiguousarray(arr)
+    if not compression and arr.dtype == np.uint16 and arr.ndim == 2 and arr.nbytes < 2 ** 32 - 1024:
+        return _encode_plain_u16(arr)
     im = Image.fromarray(arr)
     buf = io.BytesIO()
     if compression:
