@@ -220,25 +220,25 @@ LZW_HD uint32_t encode_strip(const uint8_t* in, uint32_t n, uint8_t* out, uint32
           if (p + 2u < n) ahead = in[p + 2u];
         }
       }
+      // one probe per call, written without branches: the three outcomes (hit -> next byte, free slot
+      // -> the phrase ends, other key -> next slot) would otherwise serialise the lanes
       auto probe = [&]() {
-        if (st == 0u) {
-          const uint32_t s = table[h];
-          if ((s >> 12) == key) {
-            node = s & 0xFFFu;
-            ++d;
-            if (p + d >= n) {
-              st = 2;
-            } else {
-              key = (node << 8) | ahead;
-              h = slot_of(key);
-              if (p + d + 1u < n) ahead = in[p + d + 1u];
-            }
-          } else if (s == ENC_EMPTY) {
-            st = 1;
-          } else {
-            h = h + 1u == ENC_SLOTS ? 0u : h + 1u;
-          }
+        const bool on = st == 0u;
+        const uint32_t s = table[h];
+        const bool hit = on && (s >> 12) == key;
+        const bool stop = on && !hit && s == (uint32_t)ENC_EMPTY;
+        if (hit) {
+          node = s & 0xFFFu;
+          ++d;
         }
+        const bool end = hit && p + d >= n;
+        const uint32_t nkey = (node << 8) | ahead;
+        const uint32_t nslot = slot_of(nkey);
+        const uint32_t step = h + 1u == ENC_SLOTS ? 0u : h + 1u;
+        key = hit ? nkey : key;
+        h = hit ? nslot : ((on && !stop) ? step : h);
+        st = stop ? 1u : (end ? 2u : st);
+        if (hit && p + d + 1u < n) ahead = in[p + d + 1u];
       };
       while (w.ballot(st == 0u)) {
         probe();
