@@ -379,11 +379,13 @@ struct BitReader {
     skew = 8u * a;
     bytes = n_in + a;
   }
-  LZW_HD uint32_t word(uint32_t idx) const {          // big-endian word idx, zero past the end
-    if (idx * 4u + 4u <= bytes) return bswap32(load_u32(base + idx * 4u));
+  // word idx as loaded (little-endian register image of the four stream bytes), zero past the end;
+  // the byte swap is left to code() so that a prefetched word is not waited for before its use
+  LZW_HD uint32_t word(uint32_t idx) const {
+    if (idx * 4u + 4u <= bytes) return load_u32(base + idx * 4u);
     uint32_t v = 0;
     for (uint32_t k = 0; k < 4u; ++k)
-      if (idx * 4u + k < bytes) v |= (uint32_t)base[idx * 4u + k] << (24u - 8u * k);
+      if (idx * 4u + k < bytes) v |= (uint32_t)base[idx * 4u + k] << (8u * k);
     return v;
   }
   // the two words that hold the code at bitpos (counted from the first byte) ...
@@ -394,7 +396,7 @@ struct BitReader {
   }
   // ... and the code itself
   LZW_HD uint32_t code(uint32_t bitpos, int width, uint32_t hi, uint32_t lo) const {
-    const uint64_t both = ((uint64_t)hi << 32) | lo;
+    const uint64_t both = ((uint64_t)bswap32(hi) << 32) | bswap32(lo);
     return (uint32_t)((both << ((bitpos + skew) & 31u)) >> (64 - width));
   }
 };
