@@ -114,7 +114,7 @@ def run(data_file, output, image_dir=None, batch=8, raw_intensities=False):
     def flush(pending):
         if not pending:
             return
-        raw = torch.from_numpy(np.stack([p[1] for p in pending])[:, :, None]).cuda()     # [F][C][1][H][W]
+        raw = torch.stack([p[1] for p in pending])[:, :, None].contiguous()               # [F][C][1][H][W], device
         ill = illum_dev if illum_dev is not None and tuple(illum_dev.shape[1:]) == tuple(raw.shape[3:]) else None
         for o in objects:
             labs = np.stack([p[2][o] for p in pending]).astype(np.int32)
@@ -137,13 +137,18 @@ def run(data_file, output, image_dir=None, batch=8, raw_intensities=False):
             if col.startswith('Metadata_') or col.startswith('FileName_') or col.startswith('PathName_'):
                 meta[col] = row[col]
         image_rows.append(meta)
-        planes = np.stack([tiffio.read(_path(row, '', c, image_dir)) for c in channels])
-        if planes.dtype != np.uint16:
-            raise ValueError("16-bit images expected (row %d)" % image_number)
+        blobs = []
+        for c in channels:
+            with open(_path(row, '', c, image_dir), 'rb') as fh:
+                blobs.append(fh.read())
+        try:
+            planes = tiffio.load_planes(blobs)                 # [C][H][W] on the device (TIFF strips decoded there, K7)
+        except ValueError as e:
+            raise ValueError("16-bit images of one shape expected (row %d): %s" % (image_number, e))
         labs = {o: tiffio.read(_path(row, 'Objects_', o, image_dir)) for o in objects}
-        if shape is not None and planes.shape != shape:
+        if shape is not None and tuple(planes.shape) != shape:
             flush(pending)
-        shape = planes.shape
+        shape = tuple(planes.shape)
         pending.append((image_number, planes, labs))
         if len(pending) == batch:
             flush(pending)
