@@ -488,7 +488,7 @@ def tiff_lzw_encode(planes, rows_per_strip=None):
 
 def tiff_lzw_decode(src, src_off, src_bytes, dst, dst_off, dst_bytes):
     """LZW strips src[src_off[s] : +src_bytes[s]] -> dst[dst_off[s] : +dst_bytes[s]] (uint8 views,
-    device).  The descriptor arrays are host sequences.  Returns the per-strip status (host
+    device).  The descriptor arrays are host sequences or NumPy arrays.  Returns the per-strip status (host
     int32 tensor; 0 = ok).  Replaces the strip decoding behind Image.open / imageio.imread
     (Image_re-binning.py:17, MaxProjection.py:39)."""
     _check(src, "src", torch.uint8, 1)
@@ -498,10 +498,8 @@ def tiff_lzw_decode(src, src_off, src_bytes, dst, dst_off, dst_bytes):
         raise ValueError("descriptor arrays differ in length")
     if n == 0:
         return torch.zeros((0,), dtype=torch.int32)
-    so = torch.as_tensor(list(src_off), dtype=torch.int64)
-    sb = torch.as_tensor(list(src_bytes), dtype=torch.int64)
-    do = torch.as_tensor(list(dst_off), dtype=torch.int64)
-    db = torch.as_tensor(list(dst_bytes), dtype=torch.int64)
+    import numpy as np
+    so, sb, do, db = (torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)) for x in (src_off, src_bytes, dst_off, dst_bytes))
     if int(so.min()) < 0 or int(sb.min()) < 0 or int((so + sb).max()) > src.numel():
         raise ValueError("a source strip lies outside src")
     if int(do.min()) < 0 or int(db.min()) < 0 or int((do + db).max()) > dst.numel():

@@ -125,6 +125,7 @@ def decode_to_device(files, device=None):
     """list of TIFF byte strings of equal shape -> uint16 CUDA tensor [P][H][W].
     Raises Unsupported (before touching the GPU) when any file is outside the device codec's
     layout, ValueError when shapes differ or a strip is corrupt."""
+    import warnings
     import torch
     from .. import ops
     infos = [parse(f) for f in files]
@@ -135,30 +136,41 @@ def decode_to_device(files, device=None):
         raise ValueError("Image shape mismatch")
     dev = torch.device(device if device is not None else "cuda")
     plane = h * w * 2
-    base, total = [], 0
-    for f in files:
-        base.append(total)
-        total += (len(f) + 15) // 16 * 16
-    host = torch.empty((total,), dtype=torch.uint8, pin_memory=True)      # staging block from torch's pinned-memory cache
-    hv = host.numpy()
-    for b, f in zip(base, files):
-        hv[b:b + len(f)] = np.frombuffer(f, dtype=np.uint8)
-    src = host.to(dev, non_blocking=True)
     out = torch.empty((len(files), h, w), dtype=torch.uint16, device=dev)
     dst = out.view(torch.uint8).reshape(-1)
+
+    def upload(view, data):            # bytes -> device, straight from the bytes object (the driver stages it once)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)          # torch.frombuffer on read-only bytes
+            view.copy_(torch.frombuffer(data, dtype=torch.uint8))
+
+    # LZW files go to a device buffer of compressed bytes; uncompressed strips straight to their pixels
+    lzw = [p for p, i in enumerate(infos) if i["compression"] == 5]
+    base = {}
+    total = 0
+    for p in lzw:
+        base[p] = total
+        total += (len(files[p]) + 15) // 16 * 16
+    src = torch.empty((max(total, 16),), dtype=torch.uint8, device=dev)
     so, sb, do, db = [], [], [], []
-    for p, (b, i) in enumerate(zip(base, infos)):
+    for p, i in enumerate(infos):
         rps = i["rows_per_strip"]
-        for s, (o, c) in enumerate(zip(i["offsets"], i["counts"])):
-            rows = min(rps, h - s * rps)
-            d0, dn = p * plane + s * rps * w * 2, rows * w * 2
-            if i["compression"] == 5:
-                so.append(b + o); sb.append(c); do.append(d0); db.append(dn)
-            else:
-                if c < dn:
-                    raise ValueError("uncompressed strip %d of file %d is short" % (s, p))
-                dst[d0:d0 + dn] = src[b + o:b + o + dn]
+        offs, cnts = np.asarray(i["offsets"], np.int64), np.asarray(i["counts"], np.int64)
+        rows = np.minimum(rps, h - rps * np.arange(len(offs), dtype=np.int64))
+        d0, dn = p * plane + rps * w * 2 * np.arange(len(offs), dtype=np.int64), rows * w * 2
+        if i["compression"] == 5:
+            upload(src[base[p]:base[p] + len(files[p])], files[p])
+            so.append(base[p] + offs); sb.append(cnts); do.append(d0); db.append(dn)
+            continue
+        if np.any(cnts < dn):
+            raise ValueError("an uncompressed strip of file %d is short" % p)
+        if np.all(offs[1:] == offs[:-1] + dn[:-1]):                 # the usual case: one run of pixels
+            upload(dst[p * plane:(p + 1) * plane], memoryview(files[p])[int(offs[0]):int(offs[0]) + plane])
+        else:
+            for o, a, n in zip(offs, d0, dn):
+                upload(dst[int(a):int(a + n)], memoryview(files[p])[int(o):int(o + n)])
     if so:
+        so, sb, do, db = (np.concatenate(x) for x in (so, sb, do, db))
         status = ops.tiff_lzw_decode(src, so, sb, dst, do, db)
         if int(status.max()) != 0:
             bad = int(torch.nonzero(status)[0])
