@@ -1,6 +1,7 @@
 """K6 / A6 / A7 timing: the QC metrics of Illumination_QC_mult.py (radial power spectrum slope +
 PercentMaximal) for one 2160^2 channel on the GPU path of the drop-in script, next to the
-reference arithmetic (oracle/qc.py = the reference's own functions restated) on one host core."""
+reference's NumPy / SciPy arithmetic (Illumination_QC_mult.py:31-125, restated below for timing)
+on one host core."""
 import json
 import sys
 import time
@@ -11,7 +12,26 @@ import torch
 sys.path.insert(0, ".")
 from image_processing_suite_b200 import synth
 from image_processing_suite_b200.scripts import Illumination_QC_mult as qc
-from oracle import qc as o_qc
+
+
+
+def cpu_qc(x):
+    """rps + slope + PercentMaximal as the reference computes them (:31-125), NumPy / SciPy on the host."""
+    import scipy.fft
+    import scipy.ndimage
+    import scipy.stats
+    h, w = x.shape
+    y = x / np.median(np.abs(x - x.mean())) if np.ptp(x) > 0 else x
+    spec = np.abs(scipy.fft.fft2(y - y.mean()))
+    di = np.minimum(np.arange(h), h - 1 - np.arange(h))
+    dj = np.minimum(np.arange(w), w - 1 - np.arange(w))
+    rings = np.floor(np.sqrt(di[:, None] ** 2 + dj[None, :] ** 2)).astype(np.int64) + 1
+    labels = np.arange(2, int(np.floor(min(h, w) / 8.0)))
+    power = np.asarray(scipy.ndimage.sum(spec ** 2, rings, labels))
+    ok = power > 0
+    slope = scipy.stats.linregress(np.log(labels[ok]), np.log(power[ok]))[0] if ok.sum() > 2 else 0.0
+    return slope, 100.0 * float(np.count_nonzero(x == x.max())) / x.size
+
 
 labs = synth.make_labels(2160, 2160, 2000, seed=3)
 raw = synth.field_numpy(labs, c=5, z=1, seed=3)[:, 0]                 # [5][2160][2160] uint16
@@ -37,8 +57,7 @@ t0 = time.perf_counter()
 ref = []
 for c in range(2):
     x = raw[c].astype(float) / ill[c]
-    r = o_qc.qc_metrics(x, "ch")
-    ref.append((r["ImageQuality_PowerLogLogSlope_ch"], r["ImageQuality_PercentMaximal_ch"]))
+    ref.append(cpu_qc(x))
 t_cpu = (time.perf_counter() - t0) / 2
 for (gs, gp), (rs, rp) in zip(got, ref):
     assert abs(gs - rs) <= 1e-9 * max(1.0, abs(rs)) and gp == rp, (gs, rs, gp, rp)
