@@ -235,6 +235,45 @@ def cpu_baseline_leg(host_ring, illum_host, budget_s=20.0):
                 n, rows, H_, cores, t, t1)}
 
 
+
+def secondary_kernels(field_u16):
+    """Short device-timed figures for the other kernels of the path (N=1, rank 0, after the timed
+    regions): the Pillow-exact LANCZOS re-binning of one 5-plane field and the TIFF-LZW strip codec
+    on its result.  Never fatal: a failure is reported as a string."""
+    import torch
+    from image_processing_suite_b200 import ops
+    try:
+        def timed(fn, iters):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+        out = {}
+        ms = timed(lambda: ops.lanczos_resize_u16(field_u16, (H_ // 2, W_ // 2)), 20)
+        out["lanczos_2160_to_1080_ms_per_field"] = ms
+        small = ops.lanczos_resize_u16(field_u16, (H_ // 2, W_ // 2)).repeat(16, 1, 1).contiguous()     # 80 planes = 16 re-binned fields
+        px = small.numel() * 2
+        ms = timed(lambda: ops.tiff_lzw_encode(small), 3)
+        out["tiff_lzw_encode_pixel_gbs"] = px / ms / 1e6
+        files, nbytes = ops.tiff_lzw_encode(small)
+        from image_processing_suite_b200.scripts import tiffio
+        blobs = [bytes(files[p, :int(n)].cpu().numpy()) for p, n in enumerate(nbytes)]
+        t0 = time.perf_counter()
+        back = tiffio.decode_to_device(blobs)
+        torch.cuda.synchronize()
+        out["tiff_lzw_decode_from_host_bytes_pixel_gbs"] = px / (time.perf_counter() - t0) / 1e9
+        out["tiff_round_trip_exact"] = bool(torch.equal(back, small))
+        out["planes"] = int(small.shape[0])
+        return out
+    except Exception as e:                                   # the headline numbers must not depend on this block
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 # ---------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------
@@ -448,6 +487,10 @@ def gpu_arm(args):
     n_obj_last = h_out[(e2e_steps - 1) % 3]["n_objects"].copy()
     pipe.close()
 
+    secondary = None
+    if rank == 0 and world == 1:
+        secondary = secondary_kernels(k1_out[0]["maxproj"][0].contiguous())
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -512,6 +555,7 @@ def gpu_arm(args):
                             "gather_bytes_per_rank": n_rows * D_row * 4 if world > 1 else 0,
                             "wells": n_wells, "wells_with_rows": int((well_count_dev > 0).sum().item())},
             "cpu_baseline": cpu,
+            "secondary": secondary,
             "clocks": clocks.summary(),
             "objects_last_field": int(n_obj_last[-1]),
         }
