@@ -436,8 +436,9 @@ def gpu_arm(args):
     launches = capi.launch_count() - l0
     ms_total = t_begin.elapsed_time(t_end)
     ms_aggregate = t_steps.elapsed_time(t_end)
-    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    k3_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    k1_all = [e[0].elapsed_time(e[1]) for e in evs]
+    k3_all = [e[1].elapsed_time(e[2]) for e in evs]
+    k1_ms, k3_ms = float(np.mean(k1_all)), float(np.mean(k3_all))
     if dist is not None:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -517,7 +518,9 @@ def gpu_arm(args):
         for name, ms in kern.items():
             nbytes = per_field[name] * Fb + ill_b
             gbs = nbytes / (ms * 1e-3) / 1e9
-            kernels[name] = {"ms_per_launch": ms, "gbs": gbs, "frac": gbs / peak,
+            per_launch = k1_all if name in ("fused", "K1") else k3_all
+            kernels[name] = {"ms_per_launch": ms, "ms_median": float(np.median(per_launch)), "ms_best": float(np.min(per_launch)),
+                             "gbs": gbs, "frac": gbs / peak,
                              "bytes_per_field": per_field[name], "illum_bytes_per_launch": ill_b,
                              "survey_8d_gbs_illum_per_field": (per_field[name] + ill_b) * Fb / (ms * 1e-3) / 1e9}
         dom = max(kern, key=kern.get)
