@@ -237,3 +237,26 @@ def test_oracle_fuzz_against_pillow():
         ref = pil_lzw(img)
         assert T.same_file(T.encode_tiff_lzw(img), ref), (trial, h, w)
         np.testing.assert_array_equal(T.decode_tiff(ref), img)
+
+
+def test_plain_writer_is_a_valid_baseline_tiff():
+    """tiffio.encode without compression (the output of the max-projection script): one strip,
+    readable by Pillow, by the oracle and by the product parser; odd sizes pad to an even IFD offset."""
+    from image_processing_suite_b200.scripts import tiffio
+    rng = np.random.default_rng(4)
+    for shape in ((1, 1), (3, 5), (7, 9), (64, 33), (200, 300)):
+        img = rng.integers(0, 65536, shape).astype(np.uint16)
+        data = tiffio.encode(img)
+        np.testing.assert_array_equal(np.asarray(Image.open(io.BytesIO(data)), dtype=np.uint16), img)
+        np.testing.assert_array_equal(T.decode_tiff(data), img)
+        info = tiffio.parse(data)
+        assert (info["width"], info["height"], info["compression"], len(info["offsets"])) == (shape[1], shape[0], 1, 1)
+        assert info["counts"][0] == img.nbytes and int.from_bytes(data[4:8], "little") % 2 == 0
+    with pytest.raises(tiffio.Unsupported):
+        tiffio.parse(data[:len(data) // 2])                 # IFD gone
+    cut = bytearray(tiffio.encode(img, "tiff_lzw"))
+    info = tiffio.parse(bytes(cut))
+    ifd = int.from_bytes(cut[4:8], "little")
+    with pytest.raises(tiffio.Unsupported):                  # a strip table that points outside the file
+        broken = bytes(cut[:ifd]) + bytes(cut[ifd:]).replace(int(info["counts"][0]).to_bytes(4, "little"), (1 << 30).to_bytes(4, "little"), 1)
+        tiffio.parse(broken)
