@@ -439,6 +439,8 @@ def gpu_arm(args):
     k1_all = [e[0].elapsed_time(e[1]) for e in evs]
     k3_all = [e[1].elapsed_time(e[2]) for e in evs]
     k1_ms, k3_ms = float(np.mean(k1_all)), float(np.mean(k3_all))
+    if os.environ.get("IPS_BENCH_DUMP"):
+        print("per-launch ms:", " ".join("%.3f" % v for v in k1_all), file=sys.stderr)
     if dist is not None:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
