@@ -160,7 +160,10 @@ def decode_to_device(files, device=None):
         d0, dn = p * plane + rps * w * 2 * np.arange(len(offs), dtype=np.int64), rows * w * 2
         if i["compression"] == 5:
             upload(src[base[p]:base[p] + len(files[p])], files[p])
-            so.append(base[p] + offs); sb.append(cnts); do.append(d0); db.append(dn)
+            so.append(base[p] + offs)
+            sb.append(cnts)
+            do.append(d0)
+            db.append(dn)
             continue
         if np.any(cnts < dn):
             raise ValueError("an uncompressed strip of file %d is short" % p)
