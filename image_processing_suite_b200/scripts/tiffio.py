@@ -1,6 +1,11 @@
-"""16-bit TIFF decode / encode for the drop-in scripts (Pillow; the reference uses imageio,
-tifffile and Pillow for the same files: MaxProjection.py:39,48, Illumination_QC_mult.py:145,
-Image_re-binning.py:17-21)."""
+"""16-bit TIFF decode / encode for the drop-in scripts (the reference uses imageio, tifffile and
+Pillow for the same files: MaxProjection.py:39,48, Illumination_QC_mult.py:145,
+Image_re-binning.py:17-21).
+
+Strips of 16-bit single-sample TIFFs (uncompressed or LZW, predictor 1 or 2, either byte order)
+are decoded and LZW-encoded on the GPU (decode_to_device / encode_lzw_from_device / load_planes,
+K7); decode() / encode() are the host side for everything else the reference accepts (PNG, JPEG,
+tiled or deflate TIFFs) and for the plain uncompressed output of the max-projection script."""
 import io
 
 import numpy as np
