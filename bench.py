@@ -345,28 +345,27 @@ def gpu_arm(args):
         n_chunks -= 1
     slots_per_chunk = n_slots // n_chunks
     chunk_fields = slots_per_chunk * Fb
-    cap = chunk_fields * n_max
-    all_rows = torch.empty((n_chunks * world, cap, D_row), dtype=torch.float32, device=dev)
-    all_counts = torch.zeros((n_chunks * world,), dtype=torch.int64, device=dev)
-    gatherer = plate_mod.RowGatherer(cap, D_row)
+    # One header-led block per (chunk, rank): row 0 carries the row count, so the gather is ONE
+    # fixed-size ncclAllGather per chunk and the launching thread never waits for the device
+    # (ips_pack_rows_block -> ips_allgather_blocks -> ips_well_sums_add_blocks).
+    block_rows = chunk_fields * n_max + 1
+    table = torch.zeros((n_chunks, world, block_rows, D_row), dtype=torch.float32, device=dev)
+    gatherer = plate_mod.BlockGatherer()
     well_agg = plate_mod.WellAggregator(n_wells, D_row, device=dev)
+    pack_ws = torch.empty(max(int(capi.call("ips_pack_rows_workspace_bytes", chunk_fields)), 16), dtype=torch.uint8, device=dev)
     agg_stream = torch.cuda.Stream(device=dev, priority=-1)   # its few CTAs must not queue behind a full fused grid
-    rows_seen = [0]
+    chunk_events = [torch.cuda.Event() for _ in range(n_chunks)]
 
     def gather_chunk(g):
-        """Fields of chunk g are done on the compute stream: pack their rows in place and
-        all-gather them on the side stream."""
-        ev = torch.cuda.Event()
-        ev.record()
+        """Fields of chunk g are done on the compute stream: pack their rows into this rank's
+        block and all-gather the chunk's blocks on the side stream.  No host synchronisation."""
+        chunk_events[g].record()
         with torch.cuda.stream(agg_stream):
-            agg_stream.wait_event(ev)
+            agg_stream.wait_event(chunk_events[g])
             fs = slice(g * chunk_fields, (g + 1) * chunk_fields)
-            mine = all_rows[g * world + rank]
-            _, total = plate_mod.pack_rows(plate_ints[fs], plate_flts[fs], plate_n[fs], field_well[fs],
-                                           field_base=g * chunk_fields, out=mine)
-            n = int(total.item())
-            rows_seen[0] += n
-            gatherer.gather(mine, n, out=(all_rows[g * world:(g + 1) * world], all_counts[g * world:(g + 1) * world]))
+            plate_mod.pack_rows_block(plate_ints[fs], plate_flts[fs], plate_n[fs], field_well[fs], table[g, rank],
+                                      field_base=g * chunk_fields, ws=pack_ws)
+            gatherer.gather(table[g])
 
     def finish_plate():
         # Per-well sums run after the last field: measured at N = 8, folding them into the side
@@ -374,11 +373,10 @@ def gpu_arm(args):
         # than the shorter tail gained (profiles/README.md).
         torch.cuda.current_stream().wait_stream(agg_stream)
         well_agg.reset()
-        well_agg.add(all_rows, all_counts)
+        well_agg.add_blocks(table.view(n_chunks * world, block_rows, D_row))
         return well_agg.finalize()
 
     def aggregate_all():
-        rows_seen[0] = 0
         for g in range(n_chunks):
             gather_chunk(g)
         return finish_plate()
@@ -421,7 +419,6 @@ def gpu_arm(args):
     l0 = capi.launch_count()
     with ClockSampler(local) as clocks:
         t_begin.record()
-        rows_seen[0] = 0
         chunks_done = 0
         for i in range(args.steps):
             step(i, evs[i])
@@ -432,9 +429,39 @@ def gpu_arm(args):
         for g in range(chunks_done, n_chunks):
             gather_chunk(g)
         well_mean_dev, well_count_dev = finish_plate()
-        n_rows = rows_seen[0]
         t_end.record()
         barrier()
+    # ---- content check of the gathered table (outside the timed region) ---------------------
+    counts_all = plate_mod.block_counts(table.view(n_chunks * world, block_rows, D_row)).view(n_chunks, world)
+    n_rows = int(counts_all[:, rank].sum().item())
+    agg_check = "ok"
+    local_rows = int(plate_n.clamp(min=0).sum().item())
+    if n_rows != local_rows:
+        agg_check = "own block counts %d != local object rows %d" % (n_rows, local_rows)
+    rows_everywhere = torch.tensor([n_rows], device=dev, dtype=torch.int64)
+    if dist is not None:
+        dist.all_reduce(rows_everywhere)
+    if int(counts_all.sum().item()) != int(rows_everywhere.item()):
+        agg_check = "gathered counts %d != sum of the ranks' rows %d" % (int(counts_all.sum().item()), int(rows_everywhere.item()))
+    # the per-well means of this rank's own wells, recomputed from its local blocks alone, must equal
+    # the ones taken from the gathered table bit for bit (the float32 sums are exact, wellmean.cu)
+    own_table = table[:, rank].contiguous()
+    well_agg.reset()
+    well_agg.add_blocks(own_table)
+    own_mean, own_count = well_agg.finalize()
+    own_wells = torch.unique(field_well.to(torch.int64))
+    if not torch.equal(well_count_dev[own_wells], own_count[own_wells]):
+        agg_check = "per-well row counts differ between the gathered table and the local rows"
+    elif not torch.equal(well_mean_dev[own_wells].view(torch.int64), own_mean[own_wells].view(torch.int64)):
+        agg_check = "per-well means differ between the gathered table and the local rows"
+    if world > 1 and agg_check == "ok":
+        # every rank must hold the same gathered means
+        digest = well_mean_dev.nan_to_num(0.0).sum().reshape(1).clone()
+        lo, hi = digest.clone(), digest.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if float(lo.item()) != float(hi.item()):
+            agg_check = "ranks disagree on the gathered per-well means"
     launches = capi.launch_count() - l0
     ms_total = t_begin.elapsed_time(t_end)
     ms_aggregate = t_steps.elapsed_time(t_end)
@@ -557,7 +584,9 @@ def gpu_arm(args):
             "kernels": kernels,
             "aggregation": {"what": "pack rows -> %s -> per-well mean, inside the timed region" % (
                                 "NCCL all-gather of the plate's object rows (ips_allgather_rows) in %d chunks on a "
-                                "side stream, overlapping the remaining fields" % n_chunks if world > 1 else "no gather at N=1"),
+                                "side stream (one fixed-size ncclAllGather per chunk, counts in block headers, no host "
+                                "sync), overlapping the remaining fields" % n_chunks if world > 1 else "no gather at N=1"),
+                            "check": agg_check,
                             "ms_after_last_step": ms_aggregate, "rows_per_rank": n_rows, "row_bytes": D_row * 4,
                             "gather_bytes_per_rank": n_rows * D_row * 4 if world > 1 else 0,
                             "wells": n_wells, "wells_with_rows": int((well_count_dev > 0).sum().item())},
@@ -580,7 +609,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: one K1+K3 pass per step (ips_field_fused); split: K1 then K3")
-    ap.add_argument("--gather-chunks", type=int, default=8, help="pieces the plate's row all-gather is issued in")
+    ap.add_argument("--gather-chunks", type=int, default=10, help="pieces the plate's row all-gather is issued in")
     ap.add_argument("--batch", type=int, default=16, help="fields per step")
     ap.add_argument("--ring", type=int, default=32, help="distinct device-resident fields")
     ap.add_argument("--e2e-batch", type=int, default=4)

@@ -83,7 +83,7 @@ def build(force=False, verbose=False):
                 print(log)
     if rebuilt or not os.path.exists(LIB):
         objs = [j[1] for j in jobs]
-        cmd = [nvcc_path()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lnccl"]
+        cmd = [nvcc_path()] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link of libips.so failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -59,6 +59,9 @@ PROTOTYPES = {
     "ips_well_sums_reset": (i, [p, sz, i, i, p]),
     "ips_well_sums_add": (i, [p, p, i64, p, sz, i, i, p]),
     "ips_well_sums_finalize": (i, [p, sz, p, p, i, i, p]),
+    "ips_well_sums_add_blocks": (i, [p, i64, i64, p, sz, i, i, p]),
+    "ips_well_mean_f64": (i, [p, p, p, p, i64, i, i, p, sz, p]),
+    "ips_well_median_f64": (i, [p, p, p, p, p, i64, i, i, p]),
     "ips_cell_crops_workspace_bytes": (sz, [i, i]),
     "ips_cell_crops": (i, [p, p, p, p, i, i, p, p, p, p, sz, i, i, i, i, i, p]),
     "ips_tiff_rows_per_strip": (i, [i, i]),
@@ -72,13 +75,18 @@ PROTOTYPES = {
     "ips_double_sigmoid_abs": (i, [p, p, i64, i, C.c_double, p]),
     "ips_pack_rows_workspace_bytes": (sz, [i]),
     "ips_pack_rows": (i, [p, p, p, p, i, p, p, i, i, i, p, sz, p]),
+    "ips_pack_rows_block": (i, [p, p, p, p, i, p, i64, i, i, i, p, sz, p]),
+    "ips_block_counts": (i, [p, p, i64, i64, i, p]),
     "ips_rows_well_ids": (i, [p, p, p, i64, i, i, p]),
     "ips_comm_unique_id_bytes": (i, []),
     "ips_comm_unique_id": (i, [p, i]),
     "ips_comm_create": (i, [C.POINTER(p), p, i, i, i]),
     "ips_comm_destroy": (i, [p]),
     "ips_allgather_rows": (i, [p, p, i64, i, p, p, i64, p]),
+    "ips_allgather_blocks": (i, [p, p, i64, i, p]),
+    "ips_comm_rank": (i, [p, C.POINTER(i), C.POINTER(i)]),
     "ips_host_alloc": (i, [C.POINTER(p), sz]),
+    "ips_host_alloc_flags": (i, [C.POINTER(p), sz, C.c_uint]),
     "ips_host_free": (i, [p]),
     "ips_pipeline_create": (i, [C.POINTER(p), i, i, i, i, i, i, i, i, i, p, f]),
     "ips_pipeline_submit": (i64, [p, p, p, p, p, p, p, p]),

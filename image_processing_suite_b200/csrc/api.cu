@@ -55,6 +55,18 @@ extern "C" int ips_host_alloc(void** out, size_t bytes) {
   return IPS_OK;
 }
 
+// flags: 1 = portable (usable from every CUDA context), 2 = write-combined (host writes, device
+// reads: the staging buffers of a producer that never reads them back).
+extern "C" int ips_host_alloc_flags(void** out, size_t bytes, unsigned flags) {
+  if (out == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_host_alloc_flags: out is NULL");
+  if (flags & ~3u) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_host_alloc_flags: unknown flags %u", flags);
+  unsigned f = cudaHostAllocDefault;
+  if (flags & 1u) f |= cudaHostAllocPortable;
+  if (flags & 2u) f |= cudaHostAllocWriteCombined;
+  IPS_CUDA_OK(cudaHostAlloc(out, bytes, f));
+  return IPS_OK;
+}
+
 extern "C" int ips_host_free(void* p) {
   if (p != nullptr) IPS_CUDA_OK(cudaFreeHost(p));
   return IPS_OK;

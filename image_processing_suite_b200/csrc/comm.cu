@@ -27,6 +27,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   bool ok = false;
 };
 
@@ -42,6 +44,8 @@ static NcclApi& nccl() {
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
   });
   return api;
@@ -131,8 +135,37 @@ extern "C" int ips_allgather_rows(void* comm, const void* local_rows, int64_t n_
     IPS_CUDA_OK(cudaMemcpyAsync(mine, local_rows, (size_t)n_local * row_bytes, cudaMemcpyDeviceToDevice, st));
   set_count_kernel<<<1, 1, 0, st>>>(c->d_counts + c->rank, n_local);
   IPS_LAUNCH_OK("set_count_kernel");
+  // counts and rows leave in one NCCL group (one launch)
+  const bool grouped = nccl().GroupStart != nullptr && nccl().GroupEnd != nullptr;
+  if (grouped) IPS_NCCL_OK(nccl().GroupStart());
   IPS_NCCL_OK(nccl().AllGather(c->d_counts + c->rank, c->d_counts, sizeof(int64_t), ncclInt8, c->nccl, st));
-  IPS_CUDA_OK(cudaMemcpyAsync(counts_dev, c->d_counts, (size_t)c->world * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   IPS_NCCL_OK(nccl().AllGather(mine, all_rows, block, ncclInt8, c->nccl, st));
+  if (grouped) IPS_NCCL_OK(nccl().GroupEnd());
+  IPS_CUDA_OK(cudaMemcpyAsync(counts_dev, c->d_counts, (size_t)c->world * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  return IPS_OK;
+}
+
+// The form the plate pipeline uses: table [world][block_rows][row_bytes], rank r's block already
+// in place (ips_pack_rows_block: header row with the row count, then the rows).  ONE ncclAllGather
+// of fixed size; the counts travel in the headers, so the launching thread never waits for the
+// device.  A caller that knows its row count may pass block_rows = 1 + that count (all ranks the
+// same value) instead of the padded capacity.
+extern "C" int ips_allgather_blocks(void* comm, void* table, int64_t block_rows, int row_bytes, ips_stream_t stream) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  if (c == nullptr || table == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_allgather_blocks: NULL argument");
+  if (block_rows < 1 || row_bytes < 8) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_allgather_blocks: block_rows=%lld row_bytes=%d",
+                                                (long long)block_rows, row_bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t block = (size_t)block_rows * row_bytes;
+  char* mine = reinterpret_cast<char*>(table) + (size_t)c->rank * block;
+  IPS_NCCL_OK(nccl().AllGather(mine, table, block, ncclInt8, c->nccl, st));
+  return IPS_OK;
+}
+
+extern "C" int ips_comm_rank(void* comm, int* rank, int* world) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  if (c == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_comm_rank: NULL communicator");
+  if (rank) *rank = c->rank;
+  if (world) *world = c->world;
   return IPS_OK;
 }

@@ -14,7 +14,7 @@ namespace ips {
 // exclusive scan of max(n_objects, 0) over F fields, single block
 __global__ void __launch_bounds__(1024)
 rows_offsets_kernel(const int32_t* __restrict__ n_objects, int64_t* __restrict__ offsets, int64_t* __restrict__ total,
-                    int F) {
+                    uint32_t* __restrict__ header, int header_words, int F) {
   __shared__ long long warp_sum[32];
   __shared__ long long carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -42,7 +42,11 @@ rows_offsets_kernel(const int32_t* __restrict__ n_objects, int64_t* __restrict__
     if (threadIdx.x == 0) carry_s = carry + tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry_s;
+  if (threadIdx.x == 0 && total != nullptr) *total = carry_s;
+  // block header (ips_pack_rows_block): row count as two 32-bit words, the rest of the row zero
+  if (header != nullptr)
+    for (int k = threadIdx.x; k < header_words; k += blockDim.x)
+      header[k] = k == 0 ? (uint32_t)(carry_s & 0xffffffffll) : k == 1 ? (uint32_t)(carry_s >> 32) : 0u;
 }
 
 __global__ void __launch_bounds__(256)
@@ -96,7 +100,7 @@ extern "C" int ips_pack_rows(const int32_t* ints, const float* flts, const int32
   if (ws == nullptr || ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "ips_pack_rows: needs %zu workspace bytes (got %zu)", need, ws_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int64_t* offsets = reinterpret_cast<int64_t*>(ws);
-  rows_offsets_kernel<<<1, 1024, 0, st>>>(n_objects, offsets, total_out, F);
+  rows_offsets_kernel<<<1, 1024, 0, st>>>(n_objects, offsets, total_out, nullptr, 0, F);
   IPS_LAUNCH_OK("rows_offsets_kernel");
   const int nf = 2 + 5 * C;
   const long long per_field = (long long)Nmax * (8 + nf);
@@ -104,6 +108,55 @@ extern "C" int ips_pack_rows(const int32_t* ints, const float* flts, const int32
   rows_pack_kernel<<<dim3(bx > 0 ? bx : 1, F), 256, 0, st>>>(ints, flts, n_objects, field_well, offsets, rows_out,
                                                             Nmax, nf, field_base);
   IPS_LAUNCH_OK("rows_pack_kernel");
+  return IPS_OK;
+}
+
+// Same rows behind a header row: block_out [block_rows][D]; row 0 = header (row count as two
+// 32-bit words, rest zero), rows 1 .. count = the objects.  This is the unit ips_allgather_blocks
+// moves: the count travels inside the block, so neither side needs a host round trip.
+extern "C" int ips_pack_rows_block(const int32_t* ints, const float* flts, const int32_t* n_objects,
+                                   const int32_t* field_well, int field_base, float* block_out, int64_t block_rows,
+                                   int Nmax, int C, int F, void* ws, size_t ws_bytes, ips_stream_t stream) {
+  if (!ints || !flts || !n_objects || !field_well || !block_out)
+    IPS_FAIL(IPS_ERR_BAD_ARG, "ips_pack_rows_block: NULL pointer argument");
+  if (F <= 0 || F > 65535 || Nmax <= 0 || C < 1 || C > 8)
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_pack_rows_block: bad shape F=%d Nmax=%d C=%d", F, Nmax, C);
+  if (block_rows - 1 < (int64_t)F * Nmax)
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_pack_rows_block: block of %lld rows cannot hold a header and %d x %d objects",
+             (long long)block_rows, F, Nmax);
+  const size_t need = ips_pack_rows_workspace_bytes(F);
+  if (ws == nullptr || ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "ips_pack_rows_block: needs %zu workspace bytes (got %zu)", need, ws_bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t* offsets = reinterpret_cast<int64_t*>(ws);
+  const int nf = 2 + 5 * C, D = 8 + nf;
+  rows_offsets_kernel<<<1, 1024, 0, st>>>(n_objects, offsets, nullptr, reinterpret_cast<uint32_t*>(block_out), D, F);
+  IPS_LAUNCH_OK("rows_offsets_kernel");
+  const long long per_field = (long long)Nmax * D;
+  const int bx = (int)((per_field + 256 * 8 - 1) / (256 * 8));
+  rows_pack_kernel<<<dim3(bx > 0 ? bx : 1, F), 256, 0, st>>>(ints, flts, n_objects, field_well, offsets, block_out + D,
+                                                            Nmax, nf, field_base);
+  IPS_LAUNCH_OK("rows_pack_kernel");
+  return IPS_OK;
+}
+
+// counts_out[b] (device int64) = header count of block b of a [n_blocks][block_rows][D] table.
+namespace ips {
+__global__ void block_counts_kernel(const float* __restrict__ table, int64_t* __restrict__ counts, long long n_blocks,
+                                    long long block_rows, int D) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(table + (size_t)b * block_rows * D);
+  counts[b] = (long long)h[0] | ((long long)h[1] << 32);
+}
+}  // namespace ips
+
+extern "C" int ips_block_counts(const float* table, int64_t* counts_out, int64_t n_blocks, int64_t block_rows, int D,
+                                ips_stream_t stream) {
+  if (!table || !counts_out) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_block_counts: NULL pointer argument");
+  if (n_blocks <= 0 || block_rows < 1 || D < 2) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_block_counts: bad shape");
+  block_counts_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      table, counts_out, n_blocks, block_rows, D);
+  IPS_LAUNCH_OK("block_counts_kernel");
   return IPS_OK;
 }
 

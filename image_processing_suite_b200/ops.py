@@ -281,6 +281,49 @@ def well_mean(rows, well, n_wells):
     return mean, count
 
 
+def well_mean_f64(rows, well, n_wells):
+    """As ``well_mean`` on float64 rows (the CellProfiler tables the scripts read)."""
+    _check(rows, "rows", torch.float64, 2)
+    dev = rows.device
+    _check(well, "well", torch.int32, 1, dev)
+    N, D = rows.shape
+    if well.shape[0] != N:
+        raise ValueError("one well id per row expected")
+    with torch.cuda.device(dev):
+        mean = torch.empty((n_wells, D), dtype=torch.float64, device=dev)
+        count = torch.empty((n_wells,), dtype=torch.int32, device=dev)
+        ws = _workspace(capi.call("ips_well_mean_workspace_bytes", n_wells, D), dev)
+        capi.call("ips_well_mean_f64", _ptr(rows), _ptr(well), _ptr(mean), _ptr(count), N, D, n_wells,
+                  _ptr(ws), ws.numel(), _stream(dev))
+    return mean, count
+
+
+def well_median_f64(rows, well, n_wells):
+    """Per-well median of float64 rows [N][D] (NaN skipped; mean of the two middle values):
+    ``groupby('Metadata_Well').agg('median')``, Normalize_CP_ami.py:126 with
+    ``--well_agg_func median`` (:163).  Returns (median [n_wells][D] float64, count [n_wells])."""
+    _check(rows, "rows", torch.float64, 2)
+    dev = rows.device
+    _check(well, "well", torch.int32, 1, dev)
+    N, D = rows.shape
+    if well.shape[0] != N:
+        raise ValueError("one well id per row expected")
+    with torch.cuda.device(dev):
+        # grouping the row indices by well is index plumbing (torch.sort); the selection is ours
+        w64 = well.to(torch.int64)
+        inside = (w64 >= 0) & (w64 < n_wells)
+        key = torch.where(inside, w64, torch.full_like(w64, n_wells))
+        perm = torch.sort(key, stable=True).indices.contiguous()
+        counts = torch.bincount(key, minlength=n_wells + 1)[:n_wells]
+        offsets = torch.zeros((n_wells + 1,), dtype=torch.int64, device=dev)
+        offsets[1:] = torch.cumsum(counts, 0)
+        med = torch.empty((n_wells, D), dtype=torch.float64, device=dev)
+        count = torch.empty((n_wells,), dtype=torch.int32, device=dev)
+        capi.call("ips_well_median_f64", _ptr(rows), _ptr(perm), _ptr(offsets), _ptr(med), _ptr(count), N, D,
+                  n_wells, _stream(dev))
+    return med, count
+
+
 # ---- K1 + K3 in one pass ------------------------------------------------------------------
 def field_fused(raw, illum, labels, bin=2, intensity_scale=1.0, n_max=None, want_maxproj=True,
                 want_binned=True, out=None):

@@ -14,9 +14,9 @@ from . import capi
 class _Pinned:
     """Owns one cudaHostAlloc block; arrays created on it keep it alive via .base."""
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, flags=0):
         self.ptr = C.c_void_p()
-        capi.call("ips_host_alloc", C.byref(self.ptr), max(int(nbytes), 1))
+        capi.call("ips_host_alloc_flags", C.byref(self.ptr), max(int(nbytes), 1), int(flags))
         self.nbytes = int(nbytes)
 
     def __del__(self):
@@ -27,11 +27,12 @@ class _Pinned:
             pass
 
 
-def pinned_empty(shape, dtype):
-    """Page-locked host array (uninitialised); the allocation lives as long as the array."""
+def pinned_empty(shape, dtype, flags=0):
+    """Page-locked host array (uninitialised); the allocation lives as long as the array.
+    flags: 1 = portable, 2 = write-combined (ips_host_alloc_flags)."""
     dtype = np.dtype(dtype)
     count = int(np.prod(shape))
-    blk = _Pinned(count * dtype.itemsize)
+    blk = _Pinned(count * dtype.itemsize, flags)
     buf = (C.c_char * max(blk.nbytes, 1)).from_address(blk.ptr.value)
     buf._ips_block = blk                      # arr.base -> buf -> blk keeps the memory alive
     return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)

@@ -73,6 +73,95 @@ def pack_rows(ints, flts, n_objects, field_well, field_base=0, out=None):
     return rows, total
 
 
+def pack_rows_block(ints, flts, n_objects, field_well, block, field_base=0, ws=None):
+    """Padded per-field outputs -> one header-led block ``block`` [block_rows][10 + 5C] float32
+    (device): row 0 carries the row count (two 32-bit words), rows 1..count the objects.  No host
+    synchronisation; ``block_rows - 1 >= F * Nmax``.  This is the unit ``BlockGatherer`` moves."""
+    F, n_max, _ = ints.shape
+    nf = flts.shape[2]
+    Cn = (nf - 2) // 5
+    dev = ints.device
+    if not (ints.is_cuda and flts.is_cuda and n_objects.is_cuda and field_well.is_cuda and block.is_cuda):
+        raise ValueError("pack_rows_block works on device tensors (there is no CPU path)")
+    if block.dtype != torch.float32 or block.dim() != 2 or block.shape[1] != 8 + nf or not block.is_contiguous():
+        raise ValueError("block must be contiguous float32 [block_rows][%d]" % (8 + nf))
+    with torch.cuda.device(dev):
+        if ws is None:
+            ws = torch.empty(max(int(capi.call("ips_pack_rows_workspace_bytes", F)), 16), dtype=torch.uint8, device=dev)
+        capi.call("ips_pack_rows_block", _ptr(ints), _ptr(flts), _ptr(n_objects), _ptr(field_well), int(field_base),
+                  _ptr(block), block.shape[0], n_max, Cn, F, _ptr(ws), ws.numel(), _stream(dev))
+    return block
+
+
+def block_counts(table):
+    """Header counts of a [n_blocks][block_rows][D] table of header-led blocks (int64).  Device
+    tables are read by ``ips_block_counts``; host tables (gloo tests) by reinterpreting the bytes."""
+    nb, br, D = table.shape
+    if not table.is_cuda:
+        return table[:, 0, :2].contiguous().view(torch.int32).to(torch.int64).bitwise_and(0xffffffff).mul(
+            torch.tensor([1, 1 << 32])).sum(1)
+    out = torch.empty((nb,), dtype=torch.int64, device=table.device)
+    with torch.cuda.device(table.device):
+        capi.call("ips_block_counts", _ptr(table), _ptr(out), nb, br, D, _stream(table.device))
+    return out
+
+
+class BlockGatherer:
+    """The one collective, without a host round trip: ``table`` [world][block_rows][D] float32
+    with this rank's header-led block (``pack_rows_block``) already at ``table[rank]``; after
+    ``gather`` every rank holds every block.  ONE fixed-size all-gather; the row counts travel
+    inside the blocks.
+
+    backend "ips": ``ips_allgather_blocks`` (ncclAllGather inside libips.so on its own
+    communicator; the unique id travels over the caller's torch.distributed group).  backend
+    "torch": the same exchange with torch.distributed on whatever device the tensors live on
+    (the world_size-2 gloo tests; not a product path on GPUs).
+    """
+
+    def __init__(self, group=None, backend=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.backend = backend or ("ips" if torch.cuda.is_available() else "torch")
+        self._comm = None
+        if self.backend == "ips" and self.world > 1:
+            self._comm = _make_comm(dist, group, self.rank, self.world)
+
+    def gather(self, table):
+        if table.dim() != 3 or table.shape[0] != self.world or table.dtype != torch.float32 or not table.is_contiguous():
+            raise ValueError("table must be contiguous float32 [world][block_rows][D]")
+        if self.world == 1:
+            return table
+        if self.backend == "ips":
+            dev = table.device
+            with torch.cuda.device(dev):
+                capi.call("ips_allgather_blocks", self._comm, _ptr(table), table.shape[1], table.shape[2] * 4,
+                          _stream(dev))
+            return table
+        self.dist.all_gather([table[r] for r in range(self.world)], table[self.rank].clone(), group=self.group)
+        return table
+
+    def close(self):
+        if self._comm is not None:
+            capi.call("ips_comm_destroy", self._comm)
+            self._comm = None
+
+
+def _make_comm(dist, group, rank, world):
+    n = int(capi.call("ips_comm_unique_id_bytes"))
+    buf = (C.c_char * n)()
+    if rank == 0:
+        capi.call("ips_comm_unique_id", C.cast(buf, C.c_void_p), n)
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    uid = (C.c_char * n).from_buffer_copy(box[0])
+    h = C.c_void_p()
+    capi.call("ips_comm_create", C.byref(h), C.cast(uid, C.c_void_p), n, rank, world)
+    return h
+
+
 class RowGatherer:
     """The one collective: every rank contributes ``n_local`` rows of ``D`` float32, every rank
     receives all of them as a padded table [world][cap][D] plus the per-rank counts.
@@ -93,16 +182,7 @@ class RowGatherer:
         self.backend = backend or ("ips" if torch.cuda.is_available() else "torch")
         self._comm = None
         if self.backend == "ips" and self.world > 1:
-            n = int(capi.call("ips_comm_unique_id_bytes"))
-            buf = (C.c_char * n)()
-            if self.rank == 0:
-                capi.call("ips_comm_unique_id", C.cast(buf, C.c_void_p), n)
-            box = [bytes(buf)]
-            dist.broadcast_object_list(box, src=0, group=group)
-            uid = (C.c_char * n).from_buffer_copy(box[0])
-            h = C.c_void_p()
-            capi.call("ips_comm_create", C.byref(h), C.cast(uid, C.c_void_p), n, self.rank, self.world)
-            self._comm = h
+            self._comm = _make_comm(dist, group, self.rank, self.world)
 
     def gather(self, local_rows, n_local, out=None):
         """local_rows [>= n_local][D] float32 -> (all_rows [world][cap][D], counts [world] int64).
@@ -189,6 +269,14 @@ class WellAggregator:
         with torch.cuda.device(self.dev):
             capi.call("ips_well_sums_add", _ptr(all_rows), _ptr(ids), blocks * cap, _ptr(self.ws), self.ws.numel(),
                       self.D, self.n_wells, _stream(self.dev))
+
+    def add_blocks(self, table):
+        """table [n_blocks][block_rows][D] float32 of header-led blocks (``pack_rows_block`` /
+        ``BlockGatherer``): well ids and validity come from the table itself, no id array."""
+        nb, br, D = table.shape
+        with torch.cuda.device(self.dev):
+            capi.call("ips_well_sums_add_blocks", _ptr(table), nb, br, _ptr(self.ws), self.ws.numel(), self.D,
+                      self.n_wells, _stream(self.dev))
 
     def finalize(self):
         with torch.cuda.device(self.dev):

@@ -15,7 +15,8 @@ pycytominer is not a dependency here.  ``annotate`` is restated as the inner mer
 plate map with the profiles on the well (plate-map columns first); ``normalize`` as RobustMAD
 fitted on the rows selected by the ``samples`` query -- both PARITY UNPINNED (the reference
 does not pin pycytominer and has no test for them).
-Only --well_agg_func mean has a GPU kernel; any other value is refused (no CPU fallback).
+--well_agg_func mean and median have GPU kernels; any other pandas aggregation name is refused
+(there is no CPU fallback).
 """
 import argparse
 import logging
@@ -40,24 +41,32 @@ def read_csv_from_s3(bucket_name, file_key, s3):
     return pd.read_csv(StringIO(content), sep=storage.sniff_delimiter(content))
 
 
-def well_mean_gpu(df):
+AGG_FUNCS = ("mean", "median")
+
+
+def well_agg_gpu(df, func="mean"):
     """df with a Metadata_Well column and numeric feature columns -> one row per well (sorted
-    by well, as pandas groupby does), means computed by ips_well_mean in float64."""
+    by well, as pandas groupby does), aggregated in float64 on the GPU: ``mean``
+    (ips_well_mean_f64) or ``median`` (ips_well_median_f64); NaN skipped per column as pandas
+    does, any number of columns."""
     import torch
     from .. import ops
+    if func not in AGG_FUNCS:
+        raise ValueError("--well_agg_func %r has no GPU kernel (have: %s); there is no CPU fallback"
+                         % (func, ", ".join(AGG_FUNCS)))
     wells, inverse = np.unique(df["Metadata_Well"].to_numpy(), return_inverse=True)
     feats = [c for c in df.columns if c != "Metadata_Well"]
-    vals = df[feats].to_numpy(dtype=np.float64)
-    # float32 rows would lose digits the reference keeps: split every value into a float32 head
-    # and a float32 remainder and average both (the mean is linear), then add the two means
-    hi = vals.astype(np.float32)
-    lo = (vals - hi.astype(np.float64)).astype(np.float32)
+    vals = torch.from_numpy(np.ascontiguousarray(df[feats].to_numpy(dtype=np.float64))).cuda()
     ids = torch.from_numpy(inverse.astype(np.int32)).cuda()
-    mean_hi, _ = ops.well_mean(torch.from_numpy(np.ascontiguousarray(hi)).cuda(), ids, len(wells))
-    mean_lo, _ = ops.well_mean(torch.from_numpy(np.ascontiguousarray(lo)).cuda(), ids, len(wells))
-    out = pd.DataFrame((mean_hi + mean_lo).cpu().numpy(), columns=feats)
+    agg = ops.well_mean_f64 if func == "mean" else ops.well_median_f64
+    res, _ = agg(vals, ids, len(wells))
+    out = pd.DataFrame(res.cpu().numpy(), columns=feats)
     out.insert(0, "Metadata_Well", wells)
     return out
+
+
+def well_mean_gpu(df):
+    return well_agg_gpu(df, "mean")
 
 
 def annotate(profiles, platemap, join_on="Metadata_Well"):
@@ -92,10 +101,8 @@ def aggregate_table(df, prefix, qc_drop, well_agg_func):
         to_scale = [c for c in df.select_dtypes(include="integer").columns if not c.startswith("Metadata")]
         df[to_scale] = df[to_scale].multiply(df["scaling_factor"], axis=0)
         df = df.drop(columns=["scaling_factor", "Metadata_Site"])
-    if well_agg_func != "mean":
-        raise ValueError("--well_agg_func %r has no GPU kernel (only 'mean'); there is no CPU fallback" % well_agg_func)
     numeric = df.select_dtypes(include="number").columns.tolist()
-    return well_mean_gpu(df[["Metadata_Well"] + [c for c in numeric if c != "Metadata_Well"]])
+    return well_agg_gpu(df[["Metadata_Well"] + [c for c in numeric if c != "Metadata_Well"]], well_agg_func)
 
 
 def concatenate_csv_from_s3(bucket_name, plates, times, base_folder_path, output_bucket, DMSO, output_prefix,

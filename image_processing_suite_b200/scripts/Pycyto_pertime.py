@@ -40,13 +40,10 @@ def group_mean_gpu(df, keys):
     from .. import ops
     codes, uniques = pd.factorize(pd.MultiIndex.from_frame(df[keys]), sort=True)
     feats = [c for c in df.columns if c not in keys]
-    vals = df[feats].to_numpy(dtype=np.float64)
-    hi = vals.astype(np.float32)
-    lo = (vals - hi.astype(np.float64)).astype(np.float32)        # float32 head + remainder: the mean is linear
+    vals = torch.from_numpy(np.ascontiguousarray(df[feats].to_numpy(dtype=np.float64))).cuda()
     ids = torch.from_numpy(codes.astype(np.int32)).cuda()
-    m_hi, _ = ops.well_mean(torch.from_numpy(np.ascontiguousarray(hi)).cuda(), ids, len(uniques))
-    m_lo, _ = ops.well_mean(torch.from_numpy(np.ascontiguousarray(lo)).cuda(), ids, len(uniques))
-    out = pd.DataFrame((m_hi + m_lo).cpu().numpy(), columns=feats)
+    means, _ = ops.well_mean_f64(vals, ids, len(uniques))
+    out = pd.DataFrame(means.cpu().numpy(), columns=feats)
     key_df = uniques.to_frame(index=False)
     key_df.columns = keys
     return pd.concat([key_df, out], axis=1)

@@ -182,7 +182,11 @@ int ips_cosine_triu_pairs(const float* X, const int32_t* group, int n_groups, do
  * Replaces  df.groupby("Metadata_Well").agg("mean")    Normalize_CP_ami.py:126,
  *                                                       Pycyto_pertime.py:69-72
  * rows [N][D] float32, well [N] int32 in [0, n_wells) -> mean_out [n_wells][D] float64,
- * count_out [n_wells] int32 (wells without rows get NaN means, as an absent group).
+ * count_out [n_wells] int32 = rows of the well (wells without rows get NaN means, as an absent
+ * group).  NaN values are skipped per column, as pandas does: every (well, column) divides by
+ * its own count of non-NaN values (all-NaN -> NaN).  Any D.  Float32 rows are accumulated exactly
+ * (one float64 accumulator per group of 8 binades), so the result does not depend on the order
+ * in which rows, chunks or ranks arrive (up to 2^22 values per well, column and exponent class).
  */
 size_t ips_well_mean_workspace_bytes(int n_wells, int D);
 int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
@@ -194,6 +198,21 @@ int ips_well_sums_add(const float* rows, const int32_t* well, int64_t N, void* w
                       int D, int n_wells, ips_stream_t stream);
 int ips_well_sums_finalize(const void* ws, size_t ws_bytes, double* mean_out, int32_t* count_out,
                            int D, int n_wells, ips_stream_t stream);
+/* Add a table of header-led blocks [n_blocks][block_rows][D] as ips_pack_rows_block writes and
+ * ips_allgather_blocks gathers them: the well id of a row is its column 0, the valid rows of a
+ * block are the first <header count> behind its header row.  No id array, no host-side counts. */
+int ips_well_sums_add_blocks(const float* table, int64_t n_blocks, int64_t block_rows, void* ws,
+                             size_t ws_bytes, int D, int n_wells, ips_stream_t stream);
+/* The same aggregation on float64 rows (the CellProfiler tables the scripts read; ordinary
+ * float64 atomics), and  df.groupby(...).agg("median")  (--well_agg_func median,
+ * Normalize_CP_ami.py:126,163): perm [N] int64 = row indices grouped by well, offsets
+ * [n_wells + 1] int64 = group boundaries in perm; exact (radix select), NaN skipped, mean of the
+ * two middle values for even counts. */
+int ips_well_mean_f64(const double* rows, const int32_t* well, double* mean_out, int32_t* count_out,
+                      int64_t N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream);
+int ips_well_median_f64(const double* rows, const int64_t* perm, const int64_t* offsets,
+                        double* median_out, int32_t* count_out, int64_t N, int D, int n_wells,
+                        ips_stream_t stream);
 
 /* ---- centroid-centred masked cell crops, scaled to 8 bit -----------------------------------
  * Replaces the per-cell loop of Cellpose_GPU_s3fs.py:149-182 and scale_to_8bit (:34-43).
@@ -273,6 +292,15 @@ size_t ips_pack_rows_workspace_bytes(int F);
 int ips_pack_rows(const int32_t* ints, const float* flts, const int32_t* n_objects,
                   const int32_t* field_well, int field_base, float* rows_out, int64_t* total_out,
                   int Nmax, int C, int F, void* ws, size_t ws_bytes, ips_stream_t stream);
+/* The same rows behind a header row, the unit ips_allgather_blocks moves: block_out
+ * [block_rows][D], row 0 = header (row count as two 32-bit words, rest zero), rows 1..count = the
+ * objects.  block_rows - 1 >= F * Nmax.  ips_block_counts reads the headers of a table back. */
+int ips_pack_rows_block(const int32_t* ints, const float* flts, const int32_t* n_objects,
+                        const int32_t* field_well, int field_base, float* block_out,
+                        int64_t block_rows, int Nmax, int C, int F, void* ws, size_t ws_bytes,
+                        ips_stream_t stream);
+int ips_block_counts(const float* table, int64_t* counts_out, int64_t n_blocks, int64_t block_rows,
+                     int D, ips_stream_t stream);
 /* Column 0 of a gathered [world][cap_per_rank][D] row table -> int32 well id per row, -1 for
  * the padding behind each rank's count (ips_well_mean drops ids outside [0, n_wells)). */
 int ips_rows_well_ids(const float* rows, const int64_t* counts_dev, int32_t* well_out,
@@ -293,6 +321,12 @@ int ips_comm_destroy(void* comm);
 int ips_allgather_rows(void* comm, const void* local_rows, int64_t n_local, int row_bytes,
                        void* all_rows, int64_t* counts_dev, int64_t cap_per_rank,
                        ips_stream_t stream);
+/* The plate pipeline's form: table [world][block_rows][row_bytes] with rank r's header-led block
+ * (ips_pack_rows_block) already in place; ONE ncclAllGather, the row counts travel in the
+ * headers, the launching thread never waits for the device. */
+int ips_allgather_blocks(void* comm, void* table, int64_t block_rows, int row_bytes,
+                         ips_stream_t stream);
+int ips_comm_rank(void* comm, int* rank, int* world);
 
 /* ---- host-buffer pipeline (the end-to-end call a script makes) -------------------------
  * One call = H2D of a batch of raw fields + label masks, K1, K3, D2H of max projections,
@@ -302,6 +336,8 @@ int ips_allgather_rows(void* comm, const void* local_rows, int64_t n_local, int 
  */
 typedef struct ips_pipeline ips_pipeline_t;
 int ips_host_alloc(void** out, size_t bytes);
+/* flags: 1 = portable, 2 = write-combined (host writes / device reads only). */
+int ips_host_alloc_flags(void** out, size_t bytes, unsigned flags);
 int ips_host_free(void* p);
 /* label_bytes: 2 = uint16 label masks (Cellpose's own dtype below 65536 objects,
  * Cellpose_GPU_s3fs.py:143; widened on the device), 4 = int32. */

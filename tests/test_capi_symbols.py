@@ -35,6 +35,16 @@ def test_library_exports_every_declared_symbol(lib):
     assert not missing, "libips.so lacks: %s" % missing
 
 
+def test_library_has_no_link_time_nccl_dependency(lib):
+    """NCCL is bound with dlopen at run time (csrc/comm.cu): single-GPU users without libnccl
+    must still be able to load the library."""
+    import subprocess
+    from image_processing_suite_b200 import capi
+    out = subprocess.run(["readelf", "-d", capi.LIB_PATH], capture_output=True, text=True).stdout
+    needed = [l for l in out.splitlines() if "NEEDED" in l]
+    assert needed and not any("nccl" in l for l in needed)
+
+
 def test_prototypes_cover_the_header(lib):
     from image_processing_suite_b200 import capi
     assert sorted(capi.PROTOTYPES) == _declared()

@@ -73,3 +73,90 @@ def test_mad_robustize_and_double_sigmoid_match_oracle():
     ctrl2[:4] = True
     np.testing.assert_allclose(host(ops.mad_robustize(dev(prof[:, :2].copy()), dev(ctrl2.astype(np.uint8)))),
                                o_norm.mad_robustize(prof[:, :2], ctrl2), rtol=1e-12)
+
+
+def test_well_mean_wide_table_and_nan_skipping_match_pandas():
+    """CellProfiler tables carry > 255 columns and NaN cells; pandas skips NaN per
+    column (Normalize_CP_ami.py:126).  Float32 and float64 entry points."""
+    require_gpu()
+    import pandas as pd
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(11)
+    n_wells, D, N = 17, 1031, 3000
+    wells = rng.integers(0, n_wells, N).astype(np.int32)
+    rows = (rng.normal(3.0, 2.0, (N, D)) * 10.0 ** rng.integers(-6, 7, (1, D))).astype(np.float32)
+    rows[rng.random((N, D)) < 0.02] = np.nan
+    rows[:, 5] = np.nan                                         # an all-NaN column
+    rows[wells == 3, 9] = np.nan                                # all-NaN for one well only
+    rows[7, 11] = np.inf
+    ref = pd.DataFrame(rows.astype(np.float64)).groupby(wells).mean()
+    mean, count = ops.well_mean(dev(rows), dev(wells), n_wells)
+    m = host(mean)
+    np.testing.assert_allclose(m[ref.index.to_numpy()], ref.to_numpy(), rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(host(count), np.bincount(wells, minlength=n_wells))
+    assert np.isnan(m[:, 5]).all() and np.isnan(m[3, 9]) and np.isinf(m[wells[7], 11])
+    # exact accumulation: any row order gives the same bits
+    perm = rng.permutation(N)
+    mean2, _ = ops.well_mean(dev(rows[perm]), dev(wells[perm]), n_wells)
+    np.testing.assert_array_equal(host(mean2).view(np.int64), m.view(np.int64))
+    # float64 rows
+    rows64 = rows.astype(np.float64) * (1.0 + 1e-9 * rng.random((N, D)))
+    ref64 = pd.DataFrame(rows64).groupby(wells).mean()
+    mean64, _ = ops.well_mean_f64(dev(rows64), dev(wells), n_wells)
+    np.testing.assert_allclose(host(mean64)[ref64.index.to_numpy()], ref64.to_numpy(), rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("D", [3, 40, 77])
+def test_well_median_matches_pandas(D):
+    require_gpu()
+    import pandas as pd
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(12 + D)
+    n_wells, N = 13, 4001
+    wells = rng.integers(0, n_wells, N).astype(np.int32)
+    wells[wells == 4] = 5                                       # empty well
+    rows = rng.normal(0.0, 50.0, (N, D))
+    rows[rng.random((N, D)) < 0.05] = np.nan
+    rows[:, 1] = np.round(rows[:, 1])                           # ties
+    rows[wells == 2, 0] = np.nan
+    rows[::7, 2] = -0.0
+    ref = pd.DataFrame(rows).groupby(wells).median()
+    med, count = ops.well_median_f64(dev(rows), dev(wells), n_wells)
+    m = host(med)
+    np.testing.assert_array_equal(m[ref.index.to_numpy()], ref.to_numpy())
+    assert np.isnan(m[4]).all() and host(count)[4] == 0
+    np.testing.assert_array_equal(host(count), np.bincount(wells, minlength=n_wells))
+
+
+def test_header_blocks_pack_count_and_aggregate():
+    """ips_pack_rows_block -> ips_block_counts -> ips_well_sums_add_blocks: the no-host-sync form
+    of pack_rows + well_means gives the same per-well means, bit for bit."""
+    torch = require_gpu()
+    from image_processing_suite_b200 import plate
+    rng = np.random.default_rng(21)
+    F, n_max, C = 7, 30, 3
+    nf = 2 + 5 * C
+    D = 8 + nf
+    n_obj = np.array([30, 0, 12, -1, 5, 30, 1], np.int32)
+    ints = rng.integers(0, 500, (F, n_max, 6)).astype(np.int32)
+    flts = rng.normal(10.0, 3.0, (F, n_max, nf)).astype(np.float32)
+    field_well = np.array([2, 2, 3, 3, 3, 8, 8], np.int32)
+    d = [dev(x) for x in (ints, flts, n_obj, field_well)]
+    rows, total = plate.pack_rows(*d, field_base=40)
+    n = int(total.item())
+    table = torch.zeros((3, F * n_max + 1, D), dtype=torch.float32, device="cuda")
+    table[2].fill_(float("nan"))                                # block 2 stays header-less garbage with count 0
+    table[2, 0].zero_()
+    plate.pack_rows_block(*d, table[1], field_base=40)
+    counts = host(plate.block_counts(table))
+    assert counts.tolist() == [0, n, 0]
+    assert torch.equal(table[1, 1:n + 1], rows[:n])
+    agg = plate.WellAggregator(10, D)
+    agg.add_blocks(table)
+    mean_b, count_b = agg.finalize()
+    ids = torch.full((F * n_max,), -1, dtype=torch.int32, device="cuda")
+    ids[:n] = rows[:n, 0].to(torch.int32)
+    from image_processing_suite_b200 import ops
+    mean_r, count_r = ops.well_mean(rows, ids, 10)
+    np.testing.assert_array_equal(host(mean_b).view(np.int64), host(mean_r).view(np.int64))
+    np.testing.assert_array_equal(host(count_b), host(count_r))

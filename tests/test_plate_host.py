@@ -71,3 +71,40 @@ def test_row_gather_protocol_gloo_world2(tmp_path):
     assert sorted(a["means"]) == sorted(b["means"]) == [0, 1, 2, 3, 4, 5]
     for w in a["means"]:
         np.testing.assert_array_equal(a["means"][w], b["means"][w])
+
+
+def _block_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D, cap = 7, 20
+        rng = np.random.default_rng(200 + rank)
+        n_local = 6 + 5 * rank
+        table = torch.zeros((world, cap + 1, D), dtype=torch.float32)
+        rows = torch.from_numpy(rng.normal(size=(n_local, D)).astype(np.float32))
+        table[rank, 1:n_local + 1] = rows
+        hdr = torch.tensor([n_local, 0], dtype=torch.int32).view(torch.float32)
+        table[rank, 0, :2] = hdr
+        g = plate.BlockGatherer(backend="torch")
+        g.gather(table)
+        counts = plate.block_counts(table)
+        assert counts.tolist() == [6 + 5 * r for r in range(world)]
+        assert torch.equal(table[rank, 1:n_local + 1], rows)
+        torch.save(table, os.path.join(tmp, f"b{rank}.pt"))
+        with pytest.raises(ValueError):
+            g.gather(table[:, :, :3])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_block_gather_protocol_gloo_world2(tmp_path):
+    """The header-led block exchange bench.py uses (counts travel in the blocks, no host sync)."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_block_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / "b0.pt")
+    b = torch.load(tmp_path / "b1.pt")
+    assert torch.equal(a, b)
