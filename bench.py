@@ -298,18 +298,24 @@ def gpu_arm(args):
     assert R % Fb == 0, "--ring must be a multiple of --batch"
     # ---- synthetic plate shard: a ring of R distinct device-resident fields ---------------
     masks = ring_masks(R, H_, W_, NCELLS, seed=1000 * rank)
-    labels = torch.empty((R, H_, W_), dtype=torch.int32, device=dev)
+    # label masks are uint16, the dtype Cellpose writes them in (Cellpose_GPU_s3fs.py:143)
+    labels = torch.empty((R, H_, W_), dtype=torch.uint16, device=dev)
     raw = torch.empty((R, C_, Z_, H_, W_), dtype=torch.uint16, device=dev)
     for i, m in enumerate(masks):
-        labels[i].copy_(torch.from_numpy(m))
-        raw[i].copy_(synth.field_torch(labels[i], c=C_, z=Z_, seed=1000 * rank + i))
+        lab32 = torch.from_numpy(m).to(dev)
+        labels[i].copy_(lab32.to(torch.uint16))
+        raw[i].copy_(synth.field_torch(lab32, c=C_, z=Z_, seed=1000 * rank + i))
+    del lab32
     illum_host = synth.make_illum(C_, H_, W_, seed=0)
     illum = torch.from_numpy(illum_host).to(dev)
+    # once per plate: the function's reciprocal (the per-pixel divide becomes a multiply)
+    illum_rcp = ops.illum_reciprocal(illum) if args.mode == "fused" else None
     n_max = NCELLS
     scale = 1.0 / 65535.0
 
     nb = R // Fb
     fused = args.mode == "fused"
+    labels32 = None if fused else labels.to(torch.int32)      # the split K3 kernel takes int32 masks
     # object rows of the whole plate shard stay resident (they are what the all-gather moves):
     # step i writes the rows of its 16 fields into its own slice
     n_plate = min(args.steps, max(1, 4096 // Fb)) * Fb
@@ -328,11 +334,12 @@ def gpu_arm(args):
         sl = slice(b * Fb, (b + 1) * Fb)
         rows0 = {"n_objects": plate_n[:Fb], "ints": plate_ints[:Fb], "flts": plate_flts[:Fb]}
         if fused:
-            k1_out[b] = ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max, out=rows0)
+            k1_out[b] = ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max, out=rows0,
+                                        illum_rcp=illum_rcp)
             ws_f = k1_out[b]["ws"]
         else:
             k1_out[b] = ops.preprocess_fused(raw[sl], illum, bin=BIN)
-            ws_f = ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=rows0)["ws"]
+            ws_f = ops.object_stats(labels[sl].to(torch.int32), k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=rows0)["ws"]
     torch.cuda.synchronize()
     from image_processing_suite_b200 import plate as plate_mod
     D_row = 10 + 5 * C_
@@ -390,7 +397,8 @@ def gpu_arm(args):
             ev[0].record()
         if fused:
             ops.field_fused(raw[sl], illum, labels[sl], bin=BIN, intensity_scale=scale, n_max=n_max,
-                            out={"maxproj": k1_out[b]["maxproj"], "binned": k1_out[b]["binned"], **rows_out})
+                            out={"maxproj": k1_out[b]["maxproj"], "binned": k1_out[b]["binned"], **rows_out},
+                            illum_rcp=illum_rcp)
             if ev is not None:
                 ev[1].record()
                 ev[2].record()
@@ -398,7 +406,7 @@ def gpu_arm(args):
         ops.preprocess_fused(raw[sl], illum, bin=BIN, out=k1_out[b])
         if ev is not None:
             ev[1].record()
-        ops.object_stats(labels[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=rows_out)
+        ops.object_stats(labels32[sl], k1_out[b]["maxproj"], illum, scale, n_max=n_max, out=rows_out)
         if ev is not None:
             ev[2].record()
 
@@ -431,6 +439,7 @@ def gpu_arm(args):
         well_mean_dev, well_count_dev = finish_plate()
         t_end.record()
         barrier()
+    launches = capi.launch_count() - l0
     # ---- content check of the gathered table (outside the timed region) ---------------------
     counts_all = plate_mod.block_counts(table.view(n_chunks * world, block_rows, D_row)).view(n_chunks, world)
     n_rows = int(counts_all[:, rank].sum().item())
@@ -462,7 +471,6 @@ def gpu_arm(args):
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         if float(lo.item()) != float(hi.item()):
             agg_check = "ranks disagree on the gathered per-well means"
-    launches = capi.launch_count() - l0
     ms_total = t_begin.elapsed_time(t_end)
     ms_aggregate = t_steps.elapsed_time(t_end)
     k1_all = [e[0].elapsed_time(e[1]) for e in evs]
@@ -477,6 +485,25 @@ def gpu_arm(args):
     fields_total = args.steps * Fb * world
     value = fields_total / (ms_total * 1e-3)
 
+    # ---- sustained figure: one whole 3456-field plate (216 launches) back to back --------------
+    # (outside the timed region; the board settles under its power limit some 40 ms into a run,
+    # so a 20-step region is a burst figure -- profiles/README.md)
+    sustained_ms = None
+    if True:
+        n_sus = args.sustained_steps
+        if n_sus > 0:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sus = []
+            torch.cuda.synchronize()
+            for i in range(n_sus):
+                ev3 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                step(i, ev3)
+                sus.append(ev3)
+            torch.cuda.synchronize()
+            per = [e[0].elapsed_time(e[1]) if fused else e[0].elapsed_time(e[2]) for e in sus]
+            sustained_ms = {"mean": float(np.mean(per)), "last_quarter": float(np.mean(per[-max(1, n_sus // 4):])),
+                            "steps": n_sus}
+
     # ---- end to end through the host-buffer pipeline -------------------------------------
     e2e = None
     Fe = args.e2e_batch
@@ -490,32 +517,75 @@ def gpu_arm(args):
         for k in range(Fe):
             src = (j * Fe + k) % R
             h_raw[j][k] = raw[src].cpu().numpy()
-            h_lab[j][k] = labels[src].cpu().numpy().astype(np.uint16)
+            h_lab[j][k] = labels[src].cpu().numpy()
     h_out = [pipe.output_buffers() for _ in range(3)]
+    h_rows = [{k: v for k, v in o.items() if k in ("n_objects", "ints", "flts")} for o in h_out]
     e2e_steps = max(1, args.e2e_fields // Fe)
-    for i in range(3):
-        pipe.wait(pipe.submit(h_raw[i % n_host], h_lab[i % n_host], h_out[i % 3]))
-    barrier()
+
+    def run_pipeline(outs):
+        """e2e_steps batches through the host-buffer pipeline, depth 3; seconds (max over ranks)."""
+        for i in range(3):
+            pipe.wait(pipe.submit(h_raw[i % n_host], h_lab[i % n_host], outs[i % 3]))
+        barrier()
+        t0 = time.perf_counter()
+        tickets = []
+        for i in range(e2e_steps):
+            if i >= 3:
+                pipe.wait(tickets[i - 3])                     # its host output buffers are about to be reused
+            tickets.append(pipe.submit(h_raw[i % n_host], h_lab[i % n_host], outs[i % 3]))
+        for tk in tickets[-3:]:
+            pipe.wait(tk)
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec
+
     l1 = capi.launch_count()
-    t0 = time.perf_counter()
-    tickets = []
-    for i in range(e2e_steps):
-        if i >= 3:
-            pipe.wait(tickets[i - 3])                     # its host output buffers are about to be reused
-        tickets.append(pipe.submit(h_raw[i % n_host], h_lab[i % n_host], h_out[i % 3]))
-    for tk in tickets[-3:]:
-        pipe.wait(tk)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = run_pipeline(h_out)
     e2e_launches = capi.launch_count() - l1
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": e2e_steps * Fe * world / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes(h_out[0]),
+    rows_s = run_pipeline(h_rows)
+    h2d_b, d2h_b = pipe.h2d_bytes(), pipe.d2h_bytes(h_out[0])
+    d2h_rows_b = pipe.d2h_bytes(h_rows[0])
+    # the box's bare copy ceiling for exactly these transfer sizes, all ranks at once (tools/bench_pcie.py)
+    ceiling = None
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_pcie", os.path.join(ROOT, "tools", "bench_pcie.py"))
+        bp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bp)
+        secs = bp.copy_ceiling(local, h2d_b, d2h_b, 10, barrier)
+        if dist is not None:
+            for k in secs:
+                t = torch.tensor([secs[k]], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                secs[k] = float(t.item())
+        ceiling = {"h2d_alone_gbs": world * h2d_b * 10 / secs["h2d"] / 1e9,
+                   "d2h_alone_gbs": world * d2h_b * 10 / secs["d2h"] / 1e9,
+                   "both_h2d_gbs": world * h2d_b * 10 / secs["both"] / 1e9,
+                   "both_steps_per_s": world * 10 / secs["both"]}
+    except Exception as e:                                    # the headline must not depend on this block
+        ceiling = {"error": "%s: %s" % (type(e).__name__, e)}
+    e2e_value = e2e_steps * Fe * world / e2e_s
+    h2d_gbs = e2e_value / Fe * h2d_b / 1e9
+    rows_value = e2e_steps * Fe * world / rows_s
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
            "fields_per_step": Fe, "steps": e2e_steps, "timer": "host wall clock around submit..wait (copies + kernels)",
-           "gpu_launches": e2e_launches}
+           "gpu_launches": e2e_launches,
+           "h2d_gbs": h2d_gbs,
+           "pcie_ceiling_gbs": ceiling.get("both_h2d_gbs"),
+           "frac_of_ceiling": (h2d_gbs / ceiling["both_h2d_gbs"]) if ceiling.get("both_h2d_gbs") else None,
+           "ceiling": ceiling,
+           "ceiling_note": "bare pinned cudaMemcpyAsync of the same H2D + D2H sizes on all ranks at once, no kernels "
+                           "(tools/bench_pcie.py); aggregate GB/s host -> device",
+           "rows_only": {"value": rows_value, "unit": UNIT, "d2h_bytes_per_step": d2h_rows_b,
+                         "h2d_gbs": rows_value / Fe * h2d_b / 1e9,
+                         "frac_of_h2d_alone_ceiling": (rows_value / Fe * h2d_b / 1e9 / ceiling["h2d_alone_gbs"])
+                         if ceiling.get("h2d_alone_gbs") else None,
+                         "what": "same pipeline, device -> host of the object rows only (what Feature_extraction consumes)"}}
     n_obj_last = h_out[(e2e_steps - 1) % 3]["n_objects"].copy()
     pipe.close()
 
@@ -539,7 +609,7 @@ def gpu_arm(args):
             "K1": k1_bytes_per_field(C_, Z_, H_, W_, BIN) - ill_b,
             "K3": k3_bytes_per_field(C_, H_, W_, NCELLS) - ill_b,
         }
-        per_field["fused"] = per_field["K1"] + H_ * W_ * 4 + NCELLS * (6 + 2 + 5 * C_) * 4
+        per_field["fused"] = per_field["K1"] + H_ * W_ * 2 + NCELLS * (6 + 2 + 5 * C_) * 4      # uint16 label masks
         kern = {}
         if fused:
             kern["fused"] = k1_ms
@@ -551,6 +621,13 @@ def gpu_arm(args):
             gbs = nbytes / (ms * 1e-3) / 1e9
             per_launch = k1_all if name in ("fused", "K1") else k3_all
             kernels[name] = {"ms_per_launch": ms, "ms_median": float(np.median(per_launch)), "ms_best": float(np.min(per_launch)),
+                             "frac_burst": gbs / peak,
+                             "ms_sustained": sustained_ms["mean"] if (sustained_ms and name in ("fused", "K1")) else None,
+                             "frac_sustained": (nbytes / (sustained_ms["mean"] * 1e-3) / 1e9 / peak)
+                             if (sustained_ms and name in ("fused", "K1")) else None,
+                             "frac_sustained_last_quarter": (nbytes / (sustained_ms["last_quarter"] * 1e-3) / 1e9 / peak)
+                             if (sustained_ms and name in ("fused", "K1")) else None,
+                             "sustained_steps": sustained_ms["steps"] if sustained_ms else None,
                              "gbs": gbs, "frac": gbs / peak,
                              "bytes_per_field": per_field[name], "illum_bytes_per_launch": ill_b,
                              "survey_8d_gbs_illum_per_field": (per_field[name] + ill_b) * Fb / (ms * 1e-3) / 1e9}
@@ -572,7 +649,7 @@ def gpu_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "fields_per_step": Fb, "bin": BIN, "n_cells": NCELLS,
                        "ring_fields": R, "l2": "inputs larger than L2: ring of %d distinct fields = %.1f GB" % (
-                           R, R * (C_ * Z_ * H_ * W_ * 2 + H_ * W_ * 4) / 1e9),
+                           R, R * (C_ * Z_ * H_ * W_ * 2 + H_ * W_ * 2) / 1e9),
                        "mode": args.mode,
                        "sharding": "fields by well across ranks, no data-path collective"},
             "e2e": e2e,
@@ -619,6 +696,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=120.0)
     ap.add_argument("--ref-fields", type=int, default=8, help="distinct synthetic fields the reference arm cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustained-steps", type=int, default=216,
+                    help="extra launches after the timed region for the sustained kernel figure (0 = skip)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: native libraries (NCCL prints its version banner to
     # stdout when NCCL_DEBUG is set) are pointed at stderr for the duration of the run

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "ips_object_stats": (i, [p, p, p, f, p, p, p, i, p, sz, i, i, i, i, p]),
     "ips_field_fused_workspace_bytes": (sz, [i, i, i, i, i, i]),
     "ips_field_fused": (i, [p, p, p, p, p, i, f, p, p, p, i, p, sz, i, i, i, i, i, p]),
+    "ips_field_fused_ex": (i, [p, p, i, p, i, p, p, i, f, p, p, p, i, p, sz, i, i, i, i, i, p]),
+    "ips_illum_reciprocal": (i, [p, p, i64, p]),
     "ips_illum_accumulate": (i, [p, p, i, i, i, i, p]),
     "ips_illum_finalize_workspace_bytes": (sz, [i, i, i]),
     "ips_illum_finalize": (i, [p, u64, C.c_double, C.c_double, p, p, sz, i, i, i, p]),

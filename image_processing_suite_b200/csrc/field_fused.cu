@@ -13,6 +13,8 @@
 // the channels: Z x BIN 128-bit loads of raw data and 2 x BIN of the illumination function,
 // packed-uint16 max, store of the max projection, divide, bin, store of the binned row, then
 // the lane -> warp -> CTA -> global label-keyed reduction of that channel's moments.
+#include <stdlib.h>
+
 #include "object_accum.cuh"
 
 namespace ips {
@@ -254,31 +256,58 @@ extern "C" size_t ips_field_fused_workspace_bytes(int F, int C, int H, int W, in
   return ips_object_stats_workspace_bytes(F, C, Nmax);
 }
 
-extern "C" int ips_field_fused(const uint16_t* raw, const float* illum, const int32_t* labels,
-                               uint16_t* maxproj, void* binned, int bin, float intensity_scale,
-                               int32_t* n_objects, int32_t* ints, float* flts, int Nmax, void* ws,
-                               size_t ws_bytes, int F, int C, int Z, int H, int W, ips_stream_t stream) {
-  if (!raw || !labels || !n_objects || !ints || !flts) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_field_fused: NULL pointer argument");
+namespace ips {
+int field_fused2_try(const uint16_t* raw, const float* illum, int illum_is_rcp, const void* labels, int label_bytes,
+                     uint16_t* maxproj, void* binned, int bin, float intensity_scale, int32_t* n_objects,
+                     int32_t* ints, float* flts, int Nmax, void* ws, int F, int C, int Z, int H, int W,
+                     cudaStream_t st);
+}
+
+static bool force_first_generation() {
+  static const bool v = [] {
+    const char* e = getenv("IPS_FUSED_V1");          // A/B measurements only
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
+
+static int field_fused_impl(const char* who, const uint16_t* raw, const float* illum, int illum_is_rcp,
+                            const void* labels, int label_bytes, uint16_t* maxproj, void* binned, int bin,
+                            float intensity_scale, int32_t* n_objects, int32_t* ints, float* flts, int Nmax, void* ws,
+                            size_t ws_bytes, int F, int C, int Z, int H, int W, ips_stream_t stream) {
+  if (!raw || !labels || !n_objects || !ints || !flts) IPS_FAIL(IPS_ERR_BAD_ARG, "%s: NULL pointer argument", who);
   if (F < 0 || Z <= 0 || H <= 0 || W <= 0 || Nmax <= 0)
-    IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_field_fused: bad shape F=%d Z=%d H=%d W=%d Nmax=%d", F, Z, H, W, Nmax);
-  if (C < 1 || C > OA_CMAX) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_field_fused: C must be in 1..%d (got %d)", OA_CMAX, C);
-  if (bin != 1 && bin != 2 && bin != 4) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_field_fused: bin must be 1, 2 or 4 (got %d)", bin);
-  if (H % bin || W % bin) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_field_fused: %dx%d not divisible by bin %d", H, W, bin);
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "%s: bad shape F=%d Z=%d H=%d W=%d Nmax=%d", who, F, Z, H, W, Nmax);
+  if (C < 1 || C > OA_CMAX) IPS_FAIL(IPS_ERR_BAD_SHAPE, "%s: C must be in 1..%d (got %d)", who, OA_CMAX, C);
+  if (bin != 1 && bin != 2 && bin != 4) IPS_FAIL(IPS_ERR_BAD_ARG, "%s: bin must be 1, 2 or 4 (got %d)", who, bin);
+  if (H % bin || W % bin) IPS_FAIL(IPS_ERR_BAD_SHAPE, "%s: %dx%d not divisible by bin %d", who, H, W, bin);
+  if (label_bytes != 2 && label_bytes != 4) IPS_FAIL(IPS_ERR_BAD_DTYPE, "%s: labels must be uint16 (2) or int32 (4)", who);
+  if (illum_is_rcp && illum == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "%s: reciprocal flag without a function", who);
   if (F == 0) return IPS_OK;
   const size_t need = ips_object_stats_workspace_bytes(F, C, Nmax);
-  if (ws == nullptr || ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "ips_field_fused: needs %zu workspace bytes (got %zu)", need, ws_bytes);
-  if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_field_fused: workspace not 16-byte aligned");
+  if (ws == nullptr || ws_bytes < need) IPS_FAIL(IPS_ERR_NOMEM, "%s: needs %zu workspace bytes (got %zu)", who, need, ws_bytes);
+  if (!aligned16(ws)) IPS_FAIL(IPS_ERR_BAD_ALIGN, "%s: workspace not 16-byte aligned", who);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool general_ok = label_bytes == 4 && !illum_is_rcp;
+  if (!(general_ok && force_first_generation())) {
+    const int did = field_fused2_try(raw, illum, illum_is_rcp, labels, label_bytes, maxproj, binned, bin, intensity_scale,
+                                     n_objects, ints, flts, Nmax, ws, F, C, Z, H, W, st);
+    if (did != 0) return did < 0 ? did : IPS_OK;
+  }
+  if (!general_ok)
+    IPS_FAIL(IPS_ERR_BAD_ALIGN, "%s: uint16 label masks / a reciprocal function need W %% 8 == 0, 16-byte aligned "
+             "buffers and Nmax <= 65535 (W=%d Nmax=%d)", who, W, Nmax);
+  const int32_t* labels32 = reinterpret_cast<const int32_t*>(labels);
   const bool vec = (W % 8 == 0) && aligned16(raw) && aligned16(illum) && aligned16(labels) && aligned16(maxproj) &&
                    (binned == nullptr || (reinterpret_cast<uintptr_t>(binned) & (bin == 4 ? 7u : 15u)) == 0);
   if (!vec) {
-    // shapes the 128-bit kernel does not take: same results from the two general kernels
+    // shapes the 128-bit kernels do not take: same results from the two general kernels
     uint16_t* mp = maxproj;
-    if (mp == nullptr) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_field_fused: W %% 8 != 0 or unaligned buffers need a maxproj output buffer");
+    if (mp == nullptr) IPS_FAIL(IPS_ERR_BAD_ALIGN, "%s: W %% 8 != 0 or unaligned buffers need a maxproj output buffer", who);
     int rc = ips_preprocess_fused(raw, illum, mp, nullptr, binned, bin, nullptr, nullptr, 0, F, C, Z, H, W, stream);
     if (rc != IPS_OK) return rc;
-    return ips_object_stats(labels, mp, illum, intensity_scale, n_objects, ints, flts, Nmax, ws, ws_bytes, F, C, H, W, stream);
+    return ips_object_stats(labels32, mp, illum, intensity_scale, n_objects, ints, flts, Nmax, ws, ws_bytes, F, C, H, W, stream);
   }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned long long* rec = reinterpret_cast<unsigned long long*>(ws);
   int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + k3_records_bytes_pub(F, C, Nmax));
   int rc = k3_launch_init(rec, flags, F, C, Nmax, st);
@@ -286,13 +315,13 @@ extern "C" int ips_field_fused(const uint16_t* raw, const float* illum, const in
   const int tiles_x = (W + 32 * OA_PX - 1) / (32 * OA_PX);
   const int tiles_y = (H / bin + OA_WARPS - 1) / OA_WARPS;
   const long blocks_l = (long)tiles_x * tiles_y * F;
-  if (blocks_l > 0x7fffffffL) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_field_fused: batch too large for one launch");
+  if (blocks_l > 0x7fffffffL) IPS_FAIL(IPS_ERR_BAD_SHAPE, "%s: batch too large for one launch", who);
   const int grid = (int)blocks_l;
   const bool has_illum = illum != nullptr;
 #define IPS_FF_BIN(B)                                                                                         \
   do {                                                                                                        \
-    if (has_illum) launch_fused<B, true>(Z, grid, st, raw, illum, labels, maxproj, binned, rec, flags, Nmax, F, C, H, W, tiles_x); \
-    else launch_fused<B, false>(Z, grid, st, raw, illum, labels, maxproj, binned, rec, flags, Nmax, F, C, H, W, tiles_x);          \
+    if (has_illum) launch_fused<B, true>(Z, grid, st, raw, illum, labels32, maxproj, binned, rec, flags, Nmax, F, C, H, W, tiles_x); \
+    else launch_fused<B, false>(Z, grid, st, raw, illum, labels32, maxproj, binned, rec, flags, Nmax, F, C, H, W, tiles_x);          \
   } while (0)
   if (bin == 1) IPS_FF_BIN(1);
   else if (bin == 2) IPS_FF_BIN(2);
@@ -300,4 +329,20 @@ extern "C" int ips_field_fused(const uint16_t* raw, const float* illum, const in
 #undef IPS_FF_BIN
   IPS_LAUNCH_OK("field_fused_kernel");
   return k3_launch_compact(rec, flags, n_objects, ints, flts, Nmax, F, C, intensity_scale, has_illum, st);
+}
+
+extern "C" int ips_field_fused(const uint16_t* raw, const float* illum, const int32_t* labels,
+                               uint16_t* maxproj, void* binned, int bin, float intensity_scale,
+                               int32_t* n_objects, int32_t* ints, float* flts, int Nmax, void* ws,
+                               size_t ws_bytes, int F, int C, int Z, int H, int W, ips_stream_t stream) {
+  return field_fused_impl("ips_field_fused", raw, illum, 0, labels, 4, maxproj, binned, bin, intensity_scale, n_objects,
+                          ints, flts, Nmax, ws, ws_bytes, F, C, Z, H, W, stream);
+}
+
+extern "C" int ips_field_fused_ex(const uint16_t* raw, const float* illum, int illum_is_reciprocal, const void* labels,
+                                  int label_bytes, uint16_t* maxproj, void* binned, int bin, float intensity_scale,
+                                  int32_t* n_objects, int32_t* ints, float* flts, int Nmax, void* ws, size_t ws_bytes,
+                                  int F, int C, int Z, int H, int W, ips_stream_t stream) {
+  return field_fused_impl("ips_field_fused_ex", raw, illum, illum_is_reciprocal, labels, label_bytes, maxproj, binned, bin,
+                          intensity_scale, n_objects, ints, flts, Nmax, ws, ws_bytes, F, C, Z, H, W, stream);
 }

@@ -14,8 +14,8 @@
 
 namespace ips {
 
-// uint16 label masks (what Cellpose writes when a field has < 65536 objects) are widened on the
-// device: 9.3 MB less over PCIe per 2160^2 field for 28 MB of extra HBM traffic.
+// uint16 label masks (what Cellpose writes when a field has < 65536 objects) go to the fused
+// kernel as they are; this kernel only widens them for shapes that kernel does not take.
 __global__ void __launch_bounds__(256)
 widen_labels_kernel(const uint16_t* __restrict__ in, int32_t* __restrict__ out, size_t n_words /* n / 8 */,
                     size_t n) {
@@ -49,7 +49,9 @@ struct Slot {
 struct ips_pipeline {
   int Fb, C, Z, H, W, bin, Nmax, depth, label_bytes;
   float scale;
-  float* illum = nullptr;
+  float* illum = nullptr;      // the plate's function; its reciprocal on the fast path (ips_illum_reciprocal, once)
+  bool fast = false;           // shape taken by the packed-label kernel: reciprocal function, masks as they are
+  bool native16 = false;       // ... and the masks are uint16
   size_t ws_bytes = 0;
   cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
   std::vector<ips::Slot> slots;
@@ -111,11 +113,22 @@ extern "C" int ips_pipeline_create(ips_pipeline_t** out, int fields_per_batch, i
     PIPE_CUDA_OK(cudaMalloc(&p->illum, (size_t)C * plane * sizeof(float)));
     PIPE_CUDA_OK(cudaMemcpy(p->illum, illum_host, (size_t)C * plane * sizeof(float), cudaMemcpyHostToDevice));
   }
+  // The packed-label kernel takes uint16 masks directly and the function as its reciprocal; other
+  // shapes go through the general kernels (masks widened on the device).
+  p->fast = W % 8 == 0 && Nmax <= 65535 && plane < (1ull << 31);
+  p->native16 = p->fast && label_bytes == 2;
+  if (p->fast && p->illum != nullptr) {
+    if (ips_illum_reciprocal(p->illum, p->illum, (int64_t)C * (int64_t)plane, nullptr) != IPS_OK) {
+      pipeline_free(p);
+      return IPS_ERR_CUDA;
+    }
+    PIPE_CUDA_OK(cudaDeviceSynchronize());
+  }
   p->ws_bytes = ips_field_fused_workspace_bytes(fields_per_batch, C, H, W, bin, Nmax);
   p->slots.resize(depth);
   for (Slot& s : p->slots) {
     PIPE_CUDA_OK(cudaMalloc(&s.raw, Fb * C * Z * plane * sizeof(uint16_t)));
-    PIPE_CUDA_OK(cudaMalloc(&s.labels, Fb * plane * sizeof(int32_t)));
+    if (!p->native16) PIPE_CUDA_OK(cudaMalloc(&s.labels, Fb * plane * sizeof(int32_t)));
     if (label_bytes == 2) PIPE_CUDA_OK(cudaMalloc(&s.labels16, Fb * plane * sizeof(uint16_t)));
     PIPE_CUDA_OK(cudaMalloc(&s.maxproj, Fb * C * plane * sizeof(uint16_t)));
     PIPE_CUDA_OK(cudaMalloc(&s.binned, Fb * C * (plane / (bin * bin)) * 4));
@@ -151,14 +164,19 @@ extern "C" int64_t ips_pipeline_submit(ips_pipeline_t* p, const uint16_t* raw_ho
     IPS_CUDA_OK(cudaMemcpyAsync(s.labels16, labels_host, Fb * plane * sizeof(uint16_t), cudaMemcpyHostToDevice, p->s_in));
   IPS_CUDA_OK(cudaEventRecord(s.h2d_done, p->s_in));
   IPS_CUDA_OK(cudaStreamWaitEvent(p->s_compute, s.h2d_done, 0));
-  if (p->label_bytes == 2) {
+  if (p->label_bytes == 2 && !p->native16) {
     const size_t n = Fb * plane, words = n / 8;
     widen_labels_kernel<<<(unsigned)((words + 256) / 256), 256, 0, p->s_compute>>>(s.labels16, s.labels, words, n);
     IPS_LAUNCH_OK("widen_labels_kernel");
   }
-  const int rc = ips_field_fused(s.raw, p->illum, s.labels, s.maxproj, s.binned, p->bin, p->scale,
-                                 s.n_objects, s.ints, s.flts, p->Nmax, s.ws, p->ws_bytes, p->Fb, p->C,
-                                 p->Z, p->H, p->W, p->s_compute);
+  int rc;
+  if (p->fast)
+    rc = ips_field_fused_ex(s.raw, p->illum, p->illum != nullptr, p->native16 ? (const void*)s.labels16 : (const void*)s.labels,
+                            p->native16 ? 2 : 4, s.maxproj, s.binned, p->bin, p->scale, s.n_objects, s.ints, s.flts,
+                            p->Nmax, s.ws, p->ws_bytes, p->Fb, p->C, p->Z, p->H, p->W, p->s_compute);
+  else
+    rc = ips_field_fused(s.raw, p->illum, s.labels, s.maxproj, s.binned, p->bin, p->scale, s.n_objects, s.ints,
+                         s.flts, p->Nmax, s.ws, p->ws_bytes, p->Fb, p->C, p->Z, p->H, p->W, p->s_compute);
   if (rc != IPS_OK) return rc;
   IPS_CUDA_OK(cudaEventRecord(s.compute_done, p->s_compute));
   IPS_CUDA_OK(cudaStreamWaitEvent(p->s_out, s.compute_done, 0));

@@ -325,31 +325,49 @@ def well_median_f64(rows, well, n_wells):
 
 
 # ---- K1 + K3 in one pass ------------------------------------------------------------------
+def illum_reciprocal(illum):
+    """1 / illum (IEEE division, once per plate): pass the result as ``illum_rcp`` to
+    ``field_fused`` and the per-pixel divide becomes a multiply."""
+    _check(illum, "illum", torch.float32)
+    dev = illum.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(illum)
+        capi.call("ips_illum_reciprocal", _ptr(illum), _ptr(out), illum.numel(), _stream(dev))
+    return out
+
+
 def field_fused(raw, illum, labels, bin=2, intensity_scale=1.0, n_max=None, want_maxproj=True,
-                want_binned=True, out=None):
+                want_binned=True, out=None, illum_rcp=None):
     """One pass over a batch of fields: max projection, b x b sum bin (of the corrected image
     when illum is given) and per-object statistics over the label masks.
 
-    raw [F][C][Z][H][W] uint16, illum [C][H][W] float32 or None, labels [F][H][W] int32.
+    raw [F][C][Z][H][W] uint16, illum [C][H][W] float32 or None, labels [F][H][W] int32 or
+    uint16 (Cellpose's own dtype below 65536 objects).  ``illum_rcp`` = ``illum_reciprocal(illum)``
+    may be given instead of / next to ``illum`` (computed once per plate).
     Returns dict with ``maxproj``, ``binned`` (as preprocess_fused) and ``n_objects``,
     ``ints``, ``flts`` (as object_stats).  Same results as the two separate calls.
     """
     _check(raw, "raw", torch.uint16, 5)
     dev = raw.device
     F, Cn, Z, H, W = raw.shape
-    _check(labels, "labels", torch.int32, 3, dev)
+    if not isinstance(labels, torch.Tensor) or labels.dtype not in (torch.int32, torch.uint16):
+        raise TypeError("labels must be an int32 or uint16 tensor")
+    _check(labels, "labels", labels.dtype, 3, dev)
     if tuple(labels.shape) != (F, H, W):
         raise ValueError("labels shape %s does not match raw %s" % (tuple(labels.shape), tuple(raw.shape)))
-    if illum is not None:
-        _check(illum, "illum", torch.float32, 3, dev)
-        if tuple(illum.shape) != (Cn, H, W):
+    func, is_rcp = illum, 0
+    if illum_rcp is not None:
+        func, is_rcp = illum_rcp, 1
+    if func is not None:
+        _check(func, "illum", torch.float32, 3, dev)
+        if tuple(func.shape) != (Cn, H, W):
             raise ValueError("illum shape mismatch")
     if bin not in (1, 2, 4):
         raise ValueError("bin must be 1, 2 or 4")
     if H % bin or W % bin:
         raise ValueError("image size %dx%d is not divisible by bin %d" % (H, W, bin))
     if n_max is None:
-        n_max = int(labels.max().item()) if labels.numel() else 0
+        n_max = int(labels.to(torch.int32).max().item()) if labels.numel() else 0
     n_max = max(int(n_max), 1)
     out = dict(out or {})
     with torch.cuda.device(dev):
@@ -359,7 +377,7 @@ def field_fused(raw, illum, labels, bin=2, intensity_scale=1.0, n_max=None, want
         bn = out.get("binned")
         if bn is None and want_binned:
             bn = torch.empty((F, Cn, H // bin, W // bin),
-                             dtype=torch.float32 if illum is not None else torch.uint32, device=dev)
+                             dtype=torch.float32 if func is not None else torch.uint32, device=dev)
         n_obj = out.get("n_objects")
         if n_obj is None:
             n_obj = torch.empty((F,), dtype=torch.int32, device=dev)
@@ -374,9 +392,9 @@ def field_fused(raw, illum, labels, bin=2, intensity_scale=1.0, n_max=None, want
         if ws is None or ws.numel() < ws_bytes:
             ws = _workspace(ws_bytes, dev)
         if F > 0:
-            capi.call("ips_field_fused", _ptr(raw), _ptr(illum), _ptr(labels), _ptr(mp), _ptr(bn), bin,
-                      float(intensity_scale), _ptr(n_obj), _ptr(ints), _ptr(flts), n_max, _ptr(ws),
-                      ws.numel(), F, Cn, Z, H, W, _stream(dev))
+            capi.call("ips_field_fused_ex", _ptr(raw), _ptr(func), is_rcp, _ptr(labels), labels.element_size(),
+                      _ptr(mp), _ptr(bn), bin, float(intensity_scale), _ptr(n_obj), _ptr(ints), _ptr(flts), n_max,
+                      _ptr(ws), ws.numel(), F, Cn, Z, H, W, _stream(dev))
     return {"maxproj": mp, "binned": bn, "n_objects": n_obj, "ints": ints, "flts": flts, "ws": ws}
 
 

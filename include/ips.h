@@ -111,6 +111,20 @@ int ips_field_fused(const uint16_t* raw, const float* illum, const int32_t* labe
                     int32_t* n_objects, int32_t* ints, float* flts, int Nmax, void* ws,
                     size_t ws_bytes, int F, int C, int Z, int H, int W, ips_stream_t stream);
 
+/* The same pass with the inputs as they really arrive: label masks as uint16 (label_bytes 2, the
+ * dtype Cellpose writes below 65536 objects, Cellpose_GPU_s3fs.py:143) or int32 (4), and the
+ * illumination function optionally as its reciprocal (illum_is_reciprocal != 0: the per-pixel
+ * divide becomes a multiply; ips_illum_reciprocal computes 1 / illum once per plate with IEEE
+ * division).  uint16 masks and reciprocal functions need W % 8 == 0, 16-byte aligned buffers and
+ * Nmax <= 65535.  Float features are not bit-reproducible from run to run (float64 atomics in
+ * arrival order); integer features are. */
+int ips_field_fused_ex(const uint16_t* raw, const float* illum, int illum_is_reciprocal,
+                       const void* labels, int label_bytes, uint16_t* maxproj, void* binned, int bin,
+                       float intensity_scale, int32_t* n_objects, int32_t* ints, float* flts,
+                       int Nmax, void* ws, size_t ws_bytes, int F, int C, int Z, int H, int W,
+                       ips_stream_t stream);
+int ips_illum_reciprocal(const float* illum, float* rcp_out, int64_t n, ips_stream_t stream);
+
 /* ---- K2: per-plate illumination-function estimation ----------------------------------
  * Produces the {ch}_illum.npy functions that Illumination_QC_mult.py:186-193 and
  * Cellpose_GPU_s3fs.py:56 load (the reference computes them outside the repository).

@@ -10,11 +10,14 @@ from tests.gpu_util import require_gpu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("with_illum,label_dtype", [(True, np.int32), (False, np.int32), (True, np.uint16)])
-def test_pipeline_batches_match_oracle(with_illum, label_dtype):
+@pytest.mark.parametrize("with_illum,label_dtype,W", [(True, np.int32, 128), (False, np.int32, 128), (True, np.uint16, 128),
+                                                      (False, np.uint16, 128), (True, np.uint16, 100)])
+def test_pipeline_batches_match_oracle(with_illum, label_dtype, W):
+    """W = 128: the packed-label kernel (uint16 masks as they are, reciprocal function); W = 100:
+    the general kernels behind the same call (masks widened on the device)."""
     require_gpu()
     from image_processing_suite_b200.pipeline import FieldPipeline, pinned_empty
-    Fb, C, Z, H, W, cells, n_batches = 2, 3, 3, 96, 128, 12, 5
+    Fb, C, Z, H, cells, n_batches = 2, 3, 3, 96, 12, 5
     ill = synth.make_illum(C, H, W, seed=5) if with_illum else None
     scale = 1.0 / 65535.0 if with_illum else 1.0
     pipe = FieldPipeline(Fb, C, Z, H, W, bin=2, n_max=cells, depth=2, illum=ill, intensity_scale=scale,
