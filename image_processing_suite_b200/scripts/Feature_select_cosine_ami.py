@@ -44,6 +44,16 @@ def read_csv_from_s3(bucket_name, file_key, s3=None):
     return pd.read_csv(StringIO(content), sep=storage.sniff_delimiter(content))
 
 
+def drop_rows_without_group(df):
+    """Rows with a missing group key belong to no replicate group: the reference selects groups
+    with ``==`` (Feature_select_cosine_ami.py:132-140), which never matches NaN."""
+    missing = df[GROUP_KEYS].isna().any(axis=1)
+    if missing.any():
+        logger.warning("Dropping %d rows with a missing %s", int(missing.sum()), " / ".join(GROUP_KEYS))
+        df = df[~missing]
+    return df
+
+
 def average_cosine_similarities(profiles):
     """One row per (compound, timepoint, concentration) group, in order of first appearance,
     with the mean of the strict upper triangle of the group's cosine-similarity matrix
@@ -51,11 +61,13 @@ def average_cosine_similarities(profiles):
     import torch
     from .. import ops
     cos = profiles.drop(columns=['Metadata_Plate', 'Metadata_Well'])
+    cos = drop_rows_without_group(cos)
     keys = cos[GROUP_KEYS].drop_duplicates()
     key_rows = list(keys.itertuples(index=False, name=None))
     # stable sort of the rows by group id of first appearance makes every group contiguous
     gid = pd.Series(range(len(key_rows)), index=pd.MultiIndex.from_tuples(key_rows))
     row_gid = gid.reindex(pd.MultiIndex.from_frame(cos[GROUP_KEYS])).to_numpy()
+    assert not np.isnan(row_gid.astype(np.float64)).any(), "every row must belong to a group"
     order = np.argsort(row_gid, kind="stable")
     feats = cos.drop(columns=GROUP_KEYS).fillna(0).to_numpy(dtype=np.float64)[order]
     x = torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float32)).cuda()

@@ -189,51 +189,62 @@ def process_site(site_data):
     return index, site_results
 
 
+ILLUM_FILE_PATTERNS = ("{ch}_illum.npy", "Illum{ch}.npy")      # the two names the reference accepts (:186-187)
+
+
 def load_illum_cache(illum_path, channels):
-    """{ch}_illum.npy, else Illum{ch}.npy, else None (:182-199)."""
-    cache = []
-    if not illum_path:
-        return [None] * len(channels)
-    for c in channels:
-        p1 = os.path.join(illum_path, f"{c}_illum.npy")
-        p2 = os.path.join(illum_path, f"Illum{c}.npy")
-        if os.path.exists(p1):
-            cache.append(np.load(p1))
-            logging.info(f"  Loaded {c}_illum.npy")
-        elif os.path.exists(p2):
-            cache.append(np.load(p2))
-            logging.info(f"  Loaded Illum{c}.npy")
-        else:
-            cache.append(None)
-            logging.warning(f"  Warning: No illumination file found for {c}")
-    return cache
+    """One entry per channel: the first of ``{ch}_illum.npy`` / ``Illum{ch}.npy`` found under
+    ``illum_path``, else None (the channel then stays uncorrected, :148, :199)."""
+    def find(ch):
+        for pattern in ILLUM_FILE_PATTERNS:
+            name = pattern.format(ch=ch)
+            full = os.path.join(illum_path, name)
+            if os.path.exists(full):
+                logging.info("  Loaded %s", name)
+                return np.load(full)
+        logging.warning("  Warning: No illumination file found for %s", ch)
+        return None
+    return [find(ch) if illum_path else None for ch in channels]
+
+
+def run(load_data, data_path, channels, illum_path=None, output='QC_Results.csv', threads=24):
+    """The script body: LoadData CSV in, the same table plus the ImageQuality_* / QC_Error_*
+    columns out.  Stale QC columns of an earlier run are dropped first; sites fan out over a
+    thread pool (one CUDA stream per worker) and are re-assembled by CSV index."""
+    table = pd.read_csv(load_data)
+    table = table[[c for c in table.columns if 'ImageQuality_' not in c and 'QC_Error' not in c]]
+    illum = load_illum_cache(illum_path, channels)
+    names = table[[f'FileName_{ch}' for ch in channels]]
+    sites = [(idx, [os.path.join(data_path, n) for n in row], channels, illum)
+             for idx, row in zip(names.index, names.itertuples(index=False, name=None))]
+    logging.info("Starting processing on %d sites with %d threads...", len(sites), threads)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=threads) as pool:
+        per_site = dict(pool.map(process_site, sites))
+    qc = pd.DataFrame.from_dict(per_site, orient='index').sort_index()
+    result = pd.concat([table, qc], axis=1)
+    result.to_csv(output, index=False)
+    logging.info("Done! Saved to %s", output)
+    return result
 
 
 def main(argv=None):
-    args = parse_args(argv)
+    a = parse_args(argv)
     logging.basicConfig(level=logging.INFO, format='%(asctime)s - %(message)s')
-    df = pd.read_csv(args.load_data)
-    cols_to_drop = [c for c in df.columns if 'ImageQuality_' in c or 'QC_Error' in c]
-    if cols_to_drop:
-        df = df.drop(columns=cols_to_drop)
-    channel_cols = [f'FileName_{c}' for c in args.channels]
-    illum_cache = load_illum_cache(args.illum_path, args.channels)
-    tasks = []
-    for idx, row in df.iterrows():
-        paths = [os.path.join(args.data_path, row[col]) for col in channel_cols]
-        tasks.append((idx, paths, args.channels, illum_cache))
-    logging.info(f"Starting processing on {len(tasks)} sites with {args.threads} threads...")
-    results_dict = {}
-    with concurrent.futures.ThreadPoolExecutor(max_workers=args.threads) as executor:
-        futures = {executor.submit(process_site, t): t[0] for t in tasks}
-        for future in concurrent.futures.as_completed(futures):
-            idx, res = future.result()
-            results_dict[idx] = res
-    qc_df = pd.DataFrame.from_dict(results_dict, orient='index').sort_index()
-    final_df = pd.concat([df, qc_df], axis=1)
-    final_df.to_csv(args.output, index=False)
-    logging.info(f"Done! Saved to {args.output}")
-    return final_df
+    return run(a.load_data, a.data_path, a.channels, a.illum_path, a.output, a.threads)
+
+
+def bind_reference(path):
+    """The other way to deploy: load the UNMODIFIED reference script from ``path`` and substitute
+    the GPU functions for its arithmetic (process_site, rps, calculate_saturation_cp_exact,
+    calculate_qc_metrics); its own ``main()`` / argparse / CSV handling then run as they are.
+    Returns the bound module (call ``.main()``)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("Illumination_QC_mult_reference", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    for name in ("process_site", "rps", "calculate_saturation_cp_exact", "calculate_qc_metrics"):
+        setattr(ref, name, globals()[name])
+    return ref
 
 
 if __name__ == '__main__':

@@ -103,10 +103,20 @@ def max_project_chunk(groups, bucket_name, s3_client):
     for j, st in zip(ok, stacks):
         by_shape.setdefault(tuple(st.shape), []).append((j, st))
     for items in by_shape.values():
-        proj = _project(torch.stack([st for _, st in items]))
+        # a failure while projecting, encoding or uploading is that channel group's alone, as in the
+        # reference's loop (logged, the plate goes on; MaxProjection.py:85-93)
+        try:
+            proj = _project(torch.stack([st for _, st in items]))
+        except Exception as e:
+            for j, _ in items:
+                logger.error(f"Error processing group {j}: {e}")
+            continue
         for (j, _), mp in zip(items, proj):
-            s3_client.upload_fileobj(io.BytesIO(tiffio.encode(mp)), bucket_name, modify_imagepath(groups[j][0]))
-            written += 1
+            try:
+                s3_client.upload_fileobj(io.BytesIO(tiffio.encode(mp)), bucket_name, modify_imagepath(groups[j][0]))
+                written += 1
+            except Exception as e:
+                logger.error(f"Error processing group {j}: {e}")
     return written
 
 

@@ -19,7 +19,8 @@ import numpy as np
 import pandas as pd
 
 from . import storage
-from .Feature_select_cosine_ami import GROUP_KEYS, _default_feature_select, double_sigmoid_abs
+from .Feature_select_cosine_ami import (GROUP_KEYS, _default_feature_select, double_sigmoid_abs,
+                                         drop_rows_without_group)
 from .Normalize_CP_ami import normalize_mad_robustize
 
 logger = logging.getLogger(__name__)
@@ -54,9 +55,11 @@ def group_cosine(selected):
     import torch
     from .. import ops
     cos = selected.drop(columns=[c for c in ('Metadata_Plate', 'Metadata_Well', 'Metadata_Site') if c in selected.columns])
+    cos = drop_rows_without_group(cos)
     key_rows = list(cos[GROUP_KEYS].drop_duplicates().itertuples(index=False, name=None))
     gid = pd.Series(range(len(key_rows)), index=pd.MultiIndex.from_tuples(key_rows))
     row_gid = gid.reindex(pd.MultiIndex.from_frame(cos[GROUP_KEYS])).to_numpy()
+    assert not np.isnan(row_gid.astype(np.float64)).any(), "every row must belong to a group"
     order = np.argsort(row_gid, kind="stable")
     feats = cos.drop(columns=GROUP_KEYS).fillna(0).to_numpy(dtype=np.float64)[order]
     sizes = np.bincount(row_gid, minlength=len(key_rows)).tolist()

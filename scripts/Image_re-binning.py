@@ -1,0 +1,18 @@
+#!/usr/bin/env python
+"""Image_re-binning.py -- same name, same flags, same outputs as the reference's Image_re-binning.py
+(Saguaro-Biosciences/image-processing-suite); the arithmetic runs in libips.so on the GPU.
+
+    python scripts/Image_re-binning.py --bucket_name B --image_folder path/Image/ [--resolution 1080]
+
+This file only puts the repository on sys.path and runs
+``image_processing_suite_b200.scripts.Image_rebinning`` as ``__main__``; S3 is boto3, or the directory
+``$IPS_STORAGE_ROOT/<bucket>/<key>`` when that variable is set.
+"""
+import os
+import runpy
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+if __name__ == "__main__":
+    runpy.run_module("image_processing_suite_b200.scripts.Image_rebinning", run_name="__main__", alter_sys=True)

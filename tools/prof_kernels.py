@@ -18,12 +18,16 @@ illum = torch.from_numpy(synth.make_illum(bench.C_, bench.H_, bench.W_, seed=0))
 k1 = ops.preprocess_fused(raw, illum, bin=2)
 k3 = ops.object_stats(labels, k1["maxproj"], illum, 1 / 65535.0, n_max=bench.NCELLS)
 fz = None
+labels16 = labels.to(torch.uint16)
+illum_rcp = ops.illum_reciprocal(illum)
 for it in range(4):
     if "k1" in which:
         ops.preprocess_fused(raw, illum, bin=2, out=k1)
     if "k3" in which:
         ops.object_stats(labels, k1["maxproj"], illum, 1 / 65535.0, n_max=bench.NCELLS, out=k3)
     if "fused" in which:
-        fz = ops.field_fused(raw, illum, labels, bin=2, intensity_scale=1 / 65535.0, n_max=bench.NCELLS, out=fz)
+        # as bench.py runs it: uint16 label masks, the function as its reciprocal
+        fz = ops.field_fused(raw, illum, labels16, bin=2, intensity_scale=1 / 65535.0, n_max=bench.NCELLS, out=fz,
+                             illum_rcp=illum_rcp)
 torch.cuda.synchronize()
 print("ok", which, F)
