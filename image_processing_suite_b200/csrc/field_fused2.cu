@@ -26,6 +26,8 @@
 // Replaces np.maximum.reduce (MaxProjection.py:45), img.astype(float)/illum
 // (Illumination_QC_mult.py:145-150, Cellpose_GPU_s3fs.py:72), north_star's sum re-binning and
 // the CellProfiler MeasureObject* subprocess (Feature_extraction_opt.py:166-167).
+#include <stdlib.h>
+
 #include "object_accum.cuh"
 
 namespace ips {
@@ -209,9 +211,9 @@ __device__ __forceinline__ void f2_geom_packed(unsigned m, int lane, unsigned& A
 #define F2_ADD(a, b) ((a) + (b))
 
 // Call once per lane after the labels are loaded (all 32 lanes of the warp must call).
-template <int ROWS>
+template <int ROWS, typename SH>
 __device__ __forceinline__ void f2_begin(F2Lane<ROWS>& L, unsigned (&w)[ROWS][F2_WPR], unsigned Nmax, int y0, int xw0,
-                                         OaShared& sh, unsigned long long* __restrict__ rec_f, int C,
+                                         SH& sh, unsigned long long* __restrict__ rec_f, int C,
                                          bool& overflow) {
   L.lane = threadIdx.x & 31;
   f2_analyze<ROWS>(w, Nmax, L, overflow);
@@ -235,8 +237,8 @@ __device__ __forceinline__ void f2_begin(F2Lane<ROWS>& L, unsigned (&w)[ROWS][F2
   const unsigned lt = (1u << L.lane) - 1u;
   L.rec1 = base + __popc(need1 & lt);
   L.rec2 = base + n1 + __popc(need2 & lt);
-  if (!L.lead1 || L.rec1 >= OA_CAP) L.rec1 = -1;
-  if (!L.has2 || L.rec2 >= OA_CAP) L.rec2 = -1;
+  if (!L.lead1 || L.rec1 >= SH::CAP) L.rec1 = -1;
+  if (!L.has2 || L.rec2 >= SH::CAP) L.rec2 = -1;
 
   // geometry: slot 1 through the tree in packed form, slot 2 and the remainder directly
   unsigned A, B, MN, MX;
@@ -275,24 +277,31 @@ __device__ __forceinline__ void f2_begin(F2Lane<ROWS>& L, unsigned (&w)[ROWS][F2
   }
 }
 
+// Where the lane's labels live, for the rare third-label path (everything but `elem` is uniform).
+struct F2Labels {
+  const void* base;
+  size_t elem;          // index of the window's first label
+  int label_bytes, W;
+};
 // label of pixel j of the lane's window, re-read on the rare third-label path
-__device__ __noinline__ unsigned f2_reload_label(const void* lab_lane, int label_bytes, int W, int j) {
-  const size_t e = (size_t)(j / OA_PX) * W + (j % OA_PX);
-  return label_bytes == 2 ? (unsigned)reinterpret_cast<const uint16_t*>(lab_lane)[e]
-                          : (unsigned)reinterpret_cast<const int32_t*>(lab_lane)[e];
+__device__ __noinline__ unsigned f2_reload_label(const void* base, size_t elem, int label_bytes, int W, int j) {
+  const size_t e = elem + (size_t)(j / OA_PX) * W + (j % OA_PX);
+  return label_bytes == 2 ? (unsigned)reinterpret_cast<const uint16_t*>(base)[e]
+                          : (unsigned)reinterpret_cast<const int32_t*>(base)[e];
 }
 
 // ---- one channel, float mode ---------------------------------------------------------------------
 // q[r][k]: the corrected pixels of the lane's window as packed pairs.
-template <int ROWS>
+template <int ROWS, typename SH>
 __device__ __forceinline__ void f2_channel_float(const F2Lane<ROWS>& L, int c, const u64 (&q)[ROWS][F2_WPR],
-                                                 OaShared& sh, unsigned long long* __restrict__ rec_f, int C,
-                                                 const void* lab_lane, int label_bytes, int W) {
+                                                 SH& sh, unsigned long long* __restrict__ rec_f, int C,
+                                                 const F2Labels& lab) {
   const float BIG = 3.0e38f;
   {
     // pass A: masked min / max.  nnw = -0 inside / -1 outside: q + nnw * (-BIG) and q + q * nnw.
     const u64 NBIG2 = pk2(-BIG, -BIG);
-    float lo = BIG, hi = 0.f;
+    // two independent min / max chains (the warp has few neighbours to hide a serial one behind)
+    float lo = BIG, hi = 0.f, lo_b = BIG, hi_b = 0.f;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
@@ -300,24 +309,38 @@ __device__ __forceinline__ void f2_channel_float(const F2Lane<ROWS>& L, int c, c
         float a0, a1, b0, b1;
         upk2(fma2(L.nnw[r][k], NBIG2, q[r][k]), a0, a1);
         upk2(fma2(q[r][k], L.nnw[r][k], q[r][k]), b0, b1);
-        lo = fmin3(lo, a0, a1);
-        hi = fmax3(hi, b0, b1);
+        if ((r * F2_WPR + k) & 1) {
+          lo_b = fmin3(lo_b, a0, a1);
+          hi_b = fmax3(hi_b, b0, b1);
+        } else {
+          lo = fmin3(lo, a0, a1);
+          hi = fmax3(hi, b0, b1);
+        }
       }
+    lo = fminf(lo, lo_b);
+    hi = fmaxf(hi, hi_b);
     F2_TREE(lo, fminf);
     F2_TREE(hi, fmaxf);
     // pass B around the run's minimum
     const float p = __shfl_sync(OA_FULL, lo, L.head_lane);
     const u64 NP2 = pk2(-p, -p);
-    u64 s1 = 0ull, s2 = 0ull;   // packed +0.0f pairs
+    u64 s1 = 0ull, s2 = 0ull, t1 = 0ull, t2 = 0ull;   // packed +0.0f pairs, two chains each
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int k = 0; k < F2_WPR; ++k) {
         const u64 d = add2(q[r][k], NP2);
         const u64 dm = fma2(d, L.nnw[r][k], d);
-        s1 = add2(s1, dm);
-        s2 = fma2(dm, d, s2);
+        if ((r * F2_WPR + k) & 1) {
+          t1 = add2(t1, dm);
+          t2 = fma2(dm, d, t2);
+        } else {
+          s1 = add2(s1, dm);
+          s2 = fma2(dm, d, s2);
+        }
       }
+    s1 = add2(s1, t1);
+    s2 = add2(s2, t2);
     float a1, a1b, a2, a2b;
     upk2(s1, a1, a1b);
     upk2(s2, a2, a2b);
@@ -369,7 +392,7 @@ __device__ __forceinline__ void f2_channel_float(const F2Lane<ROWS>& L, int c, c
         if ((L.m3 >> j) & 1u) {
           const float v = fv[j / OA_PX][j % OA_PX];
           const double vd = (double)v;
-          oa_flush_chan<true>(rec_f, C, (int)f2_reload_label(lab_lane, label_bytes, W, j), c,
+          oa_flush_chan<true>(rec_f, C, (int)f2_reload_label(lab.base, lab.elem, lab.label_bytes, lab.W, j), c,
                               (u64)__double_as_longlong(vd), (u64)__double_as_longlong(vd * vd),
                               __float_as_uint(v), __float_as_uint(v));
         }
@@ -396,10 +419,10 @@ __device__ __forceinline__ void f2_slot_int(unsigned m, const unsigned (&iv)[ROW
   s1 = a1; s2 = a2; mn = lo; mx = hi;
 }
 
-template <int ROWS>
+template <int ROWS, typename SH>
 __device__ __forceinline__ void f2_channel_int(const F2Lane<ROWS>& L, int c, const unsigned (&iv)[ROWS][OA_PX],
-                                               OaShared& sh, unsigned long long* __restrict__ rec_f, int C,
-                                               const void* lab_lane, int label_bytes, int W) {
+                                               SH& sh, unsigned long long* __restrict__ rec_f, int C,
+                                               const F2Labels& lab) {
   {
     u64 s1, s2;
     unsigned mn, mx;
@@ -426,132 +449,235 @@ __device__ __forceinline__ void f2_channel_int(const F2Lane<ROWS>& L, int c, con
       for (int j = 0; j < ROWS * OA_PX; ++j)
         if ((L.m3 >> j) & 1u) {
           const unsigned x = iv[j / OA_PX][j % OA_PX];
-          oa_flush_chan<false>(rec_f, C, (int)f2_reload_label(lab_lane, label_bytes, W, j), c, (u64)x,
-                               (u64)(x * x), x, x);
+          oa_flush_chan<false>(rec_f, C, (int)f2_reload_label(lab.base, lab.elem, lab.label_bytes, lab.W, j), c,
+                               (u64)x, (u64)(x * x), x, x);
         }
     }
   }
 }
 
-// ---- the kernel --------------------------------------------------------------------------------
+// ---- pieces shared by the two kernels ---------------------------------------------------------------
+// Label words of the lane's window (uint16 pairs); int32 masks are narrowed here: labels <= 0
+// are background, labels > Nmax (<= 65535) are reported and skipped.
+template <int BIN>
+__device__ __forceinline__ void f2_load_labels(unsigned (&lw)[BIN][F2_WPR], const char* lab_lane, int label_bytes,
+                                               unsigned row_b, int Nmax, bool col_ok, uint64_t pol, bool& overflow) {
+#pragma unroll
+  for (int r = 0; r < BIN; ++r) {
+    if (label_bytes == 2) {
+      const uint4 l = ldg128_stream(lab_lane + (size_t)r * row_b, pol);
+      lw[r][0] = l.x; lw[r][1] = l.y; lw[r][2] = l.z; lw[r][3] = l.w;
+    } else {
+      const uint4 l0 = ldg128_stream(lab_lane + (size_t)r * row_b * 2, pol);
+      const uint4 l1 = ldg128_stream(lab_lane + (size_t)r * row_b * 2 + 16, pol);
+      const unsigned v[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+      unsigned h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = v[i] <= (unsigned)Nmax;
+        overflow |= col_ok && !ok && (int)v[i] > 0;
+        h[i] = ok ? v[i] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < F2_WPR; ++k) lw[r][k] = h[2 * k] | (h[2 * k + 1] << 16);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BIN; ++r)
+#pragma unroll
+    for (int k = 0; k < F2_WPR; ++k)
+      if (!col_ok) lw[r][k] = 0u;      // lanes beyond the image width read a valid column group but own nothing
+}
+
+// Everything that happens to one channel of the lane's window once its pixels (m: packed uint16
+// max projection rows) and illumination values (il: function or reciprocal) are in registers:
+// divide, bin, store the binned row, fold the channel into the object records.
+template <int BIN, bool HAS_ILLUM, typename SH>
+__device__ __forceinline__ void f2_consume(const uint4 (&m)[BIN], const uint4 (&il)[BIN][2], int illum_is_rcp,
+                                           bool store_ok, char* bp, uint64_t pol_stream, const F2Lane<BIN>& L,
+                                           bool warp_fg, int c, SH& sh, unsigned long long* __restrict__ rec_f, int C,
+                                           const F2Labels& lab) {
+  constexpr int NB = OA_PX / BIN;
+  if (HAS_ILLUM) {
+    const u64 NMAGIC2 = pk2(-8388608.f, -8388608.f);
+    u64 q[BIN][F2_WPR];
+#pragma unroll
+    for (int r = 0; r < BIN; ++r) {
+      const unsigned mw[4] = {m[r].x, m[r].y, m[r].z, m[r].w};
+      unsigned rc[8] = {il[r][0].x, il[r][0].y, il[r][0].z, il[r][0].w, il[r][1].x, il[r][1].y, il[r][1].z, il[r][1].w};
+      if (!illum_is_rcp) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rc[i] = __float_as_uint(rcp_approx(__uint_as_float(rc[i])));
+      }
+#pragma unroll
+      for (int k = 0; k < F2_WPR; ++k) {
+        // 2^23 + v as float bits, then - 2^23: exact uint16 -> float without I2F
+        const u64 fl = pk2u(__byte_perm(mw[k], 0x4b000000u, 0x7610), __byte_perm(mw[k], 0x4b000000u, 0x7632));
+        q[r][k] = mul2(add2(fl, NMAGIC2), pk2u(rc[2 * k], rc[2 * k + 1]));
+      }
+    }
+    if (store_ok) {
+      float bs[NB];
+      if (BIN == 1) {
+#pragma unroll
+        for (int k = 0; k < F2_WPR; ++k) upk2(q[0][k], bs[(2 * k) % NB], bs[(2 * k + 1) % NB]);
+      } else {
+        u64 vs[F2_WPR];
+#pragma unroll
+        for (int k = 0; k < F2_WPR; ++k) {
+          vs[k] = q[0][k];
+#pragma unroll
+          for (int r = 1; r < BIN; ++r) vs[k] = add2(vs[k], q[r][k]);
+        }
+        float h[F2_WPR];
+#pragma unroll
+        for (int k = 0; k < F2_WPR; ++k) {
+          float a, b;
+          upk2(vs[k], a, b);
+          h[k] = a + b;
+        }
+        if (BIN == 2) {
+#pragma unroll
+          for (int k = 0; k < F2_WPR; ++k) bs[k % NB] = h[k];
+        } else {
+          bs[0] = h[0] + h[1];
+          bs[1 % NB] = h[2] + h[3];
+        }
+      }
+      if (NB == 8) {
+        stg128_stream(bp, make_uint4(__float_as_uint(bs[0]), __float_as_uint(bs[1 % NB]), __float_as_uint(bs[2 % NB]),
+                                     __float_as_uint(bs[3 % NB])), pol_stream);
+        stg128_stream(bp + 16, make_uint4(__float_as_uint(bs[4 % NB]), __float_as_uint(bs[5 % NB]),
+                                          __float_as_uint(bs[6 % NB]), __float_as_uint(bs[7 % NB])), pol_stream);
+      } else if (NB == 4) {
+        stg128_stream(bp, make_uint4(__float_as_uint(bs[0]), __float_as_uint(bs[1 % NB]), __float_as_uint(bs[2 % NB]),
+                                     __float_as_uint(bs[3 % NB])), pol_stream);
+      } else {
+        stg64_stream(bp, make_uint2(__float_as_uint(bs[0]), __float_as_uint(bs[1 % NB])), pol_stream);
+      }
+    }
+    if (warp_fg) f2_channel_float<BIN>(L, c, q, sh, rec_f, C, lab);
+  } else {
+    unsigned iv[BIN][OA_PX];
+#pragma unroll
+    for (int r = 0; r < BIN; ++r) unpack_u16x8(m[r], iv[r]);
+    if (store_ok) {
+      unsigned bs[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) bs[j] = 0u;
+#pragma unroll
+      for (int r = 0; r < BIN; ++r)
+#pragma unroll
+        for (int i = 0; i < OA_PX; ++i) bs[i / BIN] += iv[r][i];
+      if (NB == 8) {
+        stg128_stream(bp, make_uint4(bs[0], bs[1 % NB], bs[2 % NB], bs[3 % NB]), pol_stream);
+        stg128_stream(bp + 16, make_uint4(bs[4 % NB], bs[5 % NB], bs[6 % NB], bs[7 % NB]), pol_stream);
+      } else if (NB == 4) {
+        stg128_stream(bp, make_uint4(bs[0], bs[1 % NB], bs[2 % NB], bs[3 % NB]), pol_stream);
+      } else {
+        stg64_stream(bp, make_uint2(bs[0], bs[1 % NB]), pol_stream);
+      }
+    }
+    if (warp_fg) f2_channel_int<BIN>(L, c, iv, sh, rec_f, C, lab);
+  }
+}
+
+// ---- kernel A: direct 128-bit loads ------------------------------------------------------------------
+// Grid (F, tiles_x, tiles_y): blockIdx.x = field is the fastest index, so the F blocks that read the
+// same piece of the plate-constant illumination function are adjacent in launch order (it comes
+// from HBM once per launch and from L2 for the other fields), and no index division is needed.
+// Addressing: per-lane byte pointers for the raw stack and the function that advance by a uniform
+// stride per channel; rows and z-planes are uniform 32-bit byte offsets from them.  Lanes beyond
+// the image width read the last valid column group instead (no default values to materialise),
+// carry background labels and skip their stores.
 template <int BIN, int ZT, bool HAS_ILLUM>
 __global__ void __launch_bounds__(OA_THREADS, BIN == 4 ? 4 : 8)
 field_fused2_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ illum, int illum_is_rcp,
                     const void* __restrict__ labels, int label_bytes, uint16_t* __restrict__ maxproj,
                     void* __restrict__ binned, unsigned long long* __restrict__ rec, int* __restrict__ flags,
-                    int Nmax, int F, int C, int Z, int H, int W, int tiles_x) {
+                    int Nmax, int C, int Z, int H, int W) {
   __shared__ OaShared sh;
   oa_init_shared(sh);
-  const int bid = blockIdx.x;
-  const int f = bid % F;
-  const int t = bid / F;
-  const int tile_x = t % tiles_x, tile_y = t / tiles_x;
+  const int f = blockIdx.x, tile_x = blockIdx.y, tile_y = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = tile_y * OA_WARPS + warp;      // binned row / row block
   const int y0 = rb * BIN;
   const int xw0 = tile_x * 32 * OA_PX;
   const int g = tile_x * 32 + lane;             // 16-byte group along the row
   const int x0 = g * OA_PX;
-  const unsigned plane = (unsigned)H * (unsigned)W;   // < 2^31 (checked by the caller)
-  const bool active = x0 < W && y0 < H;         // H % BIN == 0: a row block is all in or all out
   const int nz = ZT > 0 ? ZT : Z;
-  const uint64_t pol_stream = policy_evict_first();
-  const uint64_t pol_keep = policy_evict_last();
   unsigned long long* rec_f = rec + (size_t)f * Nmax * k3_record_words(C);
-  const unsigned off = (unsigned)y0 * (unsigned)W + (unsigned)x0;   // the lane's pixel offset inside a plane
-  const char* lab_lane = reinterpret_cast<const char*>(labels) + ((size_t)f * plane + off) * (size_t)label_bytes;
-
   bool overflow = false;
-  unsigned lw[BIN][F2_WPR];
-#pragma unroll
-  for (int r = 0; r < BIN; ++r) {
-    if (active) {
-      if (label_bytes == 2) {
-        const uint4 l = ldg128_stream(lab_lane + (size_t)r * W * 2, pol_stream);
-        lw[r][0] = l.x; lw[r][1] = l.y; lw[r][2] = l.z; lw[r][3] = l.w;
-      } else {
-        const uint4 l0 = ldg128_stream(lab_lane + (size_t)r * W * 4, pol_stream);
-        const uint4 l1 = ldg128_stream(lab_lane + (size_t)r * W * 4 + 16, pol_stream);
-        // labels <= 0 are background, labels > Nmax (<= 65535) are reported and skipped
-        const unsigned v[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        unsigned h[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool ok = v[i] <= (unsigned)Nmax;
-          overflow |= !ok && (int)v[i] > 0;
-          h[i] = ok ? v[i] : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < F2_WPR; ++k) lw[r][k] = h[2 * k] | (h[2 * k + 1] << 16);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < F2_WPR; ++k) lw[r][k] = 0u;
-    }
-  }
-  // channel 0 towards L2 while the labels are analysed (one lane in four / two touches every line)
-  const uint16_t* raw_f = raw + (size_t)f * C * nz * plane;
-  if (active) {
-    if ((lane & 3) == 0) {
-      const uint16_t* rp = raw_f + off;
-      for (int z = 0; z < nz; ++z)
-#pragma unroll
-        for (int r = 0; r < BIN; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)z * plane + r * W));
-    }
-    if (HAS_ILLUM && (lane & 1) == 0) {
-#pragma unroll
-      for (int r = 0; r < BIN; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(illum + off + r * W));
-    }
-  }
+  if (y0 < H) {                                 // warp-uniform (H % BIN == 0: a row block is all in or all out)
+    const bool col_ok = x0 < W;
+    const unsigned plane = (unsigned)H * (unsigned)W;               // < 2^31 (checked by the caller)
+    const unsigned row_b = (unsigned)W * 2u, plane_b = plane * 2u;   // bytes of a uint16 row / plane
+    const unsigned off = (unsigned)y0 * (unsigned)W + (unsigned)(col_ok ? x0 : W - OA_PX);
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_keep = policy_evict_last();
+    F2Labels lab;
+    lab.base = labels; lab.elem = (size_t)f * plane + off; lab.label_bytes = label_bytes; lab.W = W;
 
-  F2Lane<BIN> L;
-  L.lane = lane;
-  unsigned wmax = 0u;
+    unsigned lw[BIN][F2_WPR];
+    f2_load_labels<BIN>(lw, reinterpret_cast<const char*>(labels) + lab.elem * (size_t)label_bytes, label_bytes, row_b,
+                        Nmax, col_ok, pol_stream, overflow);
+    // walking pointers (bytes), channel 0
+    const char* rp = reinterpret_cast<const char*>(raw) + (size_t)f * C * nz * plane_b + (size_t)off * 2;
+    const char* ip = reinterpret_cast<const char*>(illum) + (size_t)off * 4;
+    constexpr int NB = OA_PX / BIN;
+    const unsigned bplane_b = (plane / (BIN * BIN)) * 4u;
+    const unsigned boff = ((unsigned)rb * (unsigned)(W / BIN) + (unsigned)g * NB) * 4u;
+    const size_t chan_b = (size_t)nz * plane_b;
+    const bool pf_raw = (lane & 3) == 0, pf_ill = (lane & 1) == 0;
+    // channel 0 towards L2 while the labels are analysed (one lane in four / two touches every line)
+    for (int z = 0; z < nz; ++z)
 #pragma unroll
-  for (int r = 0; r < BIN; ++r)
+      for (int r = 0; r < BIN; ++r)
+        if (pf_raw) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)z * plane_b + r * row_b));
+    if (HAS_ILLUM) {
 #pragma unroll
-    for (int k = 0; k < F2_WPR; ++k) wmax |= lw[r][k];
-  const bool warp_fg = __any_sync(OA_FULL, wmax != 0u);
-  if (warp_fg) f2_begin<BIN>(L, lw, (unsigned)Nmax, y0, xw0, sh, rec_f, C, overflow);
-
-  constexpr int NB = OA_PX / BIN;
-  const u64 NMAGIC2 = pk2(-8388608.f, -8388608.f);
-  for (int c = 0; c < C; ++c) {
-    uint4 m[BIN];
-    uint4 il[BIN][2];
-#pragma unroll
-    for (int r = 0; r < BIN; ++r) {
-      m[r] = make_uint4(0u, 0u, 0u, 0u);
-      il[r][0] = il[r][1] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+      for (int r = 0; r < BIN; ++r)
+        if (pf_ill) asm volatile("prefetch.global.L2 [%0];" ::"l"(ip + r * row_b * 2));
     }
-    const size_t fc = (size_t)f * C + c;
-    if (active) {
-      const uint16_t* rp = raw_f + (size_t)c * nz * plane + off;
-      if (c + 1 < C) {   // next channel towards L2
-        if ((lane & 3) == 0) {
-          const uint16_t* np = rp + (size_t)nz * plane;
-          for (int z = 0; z < nz; ++z)
+
+    F2Lane<BIN> L;
+    L.lane = lane;
+    unsigned wany = 0u;
 #pragma unroll
-            for (int r = 0; r < BIN; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + (size_t)z * plane + r * W));
-        }
-        if (HAS_ILLUM && (lane & 1) == 0) {
-          const float* nip = illum + (size_t)(c + 1) * plane + off;
+    for (int r = 0; r < BIN; ++r)
 #pragma unroll
-          for (int r = 0; r < BIN; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(nip + r * W));
-        }
-      }
+      for (int k = 0; k < F2_WPR; ++k) wany |= lw[r][k];
+    const bool warp_fg = __any_sync(OA_FULL, wany != 0u);
+    if (warp_fg) f2_begin<BIN>(L, lw, (unsigned)Nmax, y0, xw0, sh, rec_f, C, overflow);
+
+    for (int c = 0; c < C; ++c) {
+      uint4 m[BIN];
+      uint4 il[BIN][2];
       if (ZT > 0) {
         uint4 v[BIN][ZT > 0 ? ZT : 1];
 #pragma unroll
         for (int r = 0; r < BIN; ++r)
 #pragma unroll
-          for (int z = 0; z < ZT; ++z) v[r][z] = ldg128_stream(rp + (size_t)z * plane + r * W, pol_stream);
+          for (int z = 0; z < ZT; ++z) v[r][z] = ldg128_stream(rp + (size_t)z * plane_b + r * row_b, pol_stream);
         if (HAS_ILLUM) {
-          const float* ip = illum + (size_t)c * plane + off;
 #pragma unroll
           for (int r = 0; r < BIN; ++r) {
-            il[r][0] = ldg128_keep(ip + r * W, pol_keep);
-            il[r][1] = ldg128_keep(ip + r * W + 4, pol_keep);
+            il[r][0] = ldg128_keep(ip + r * row_b * 2, pol_keep);
+            il[r][1] = ldg128_keep(ip + r * row_b * 2 + 16, pol_keep);
+          }
+        }
+        if (c + 1 < C) {   // next channel towards L2 (distance 1 measured best)
+          const char* np = rp + chan_b;
+#pragma unroll
+          for (int z = 0; z < ZT; ++z)
+#pragma unroll
+            for (int r = 0; r < BIN; ++r)
+              if (pf_raw) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + (size_t)z * plane_b + r * row_b));
+          if (HAS_ILLUM) {
+            const char* nip = ip + (size_t)plane_b * 2;
+#pragma unroll
+            for (int r = 0; r < BIN; ++r)
+              if (pf_ill) asm volatile("prefetch.global.L2 [%0];" ::"l"(nip + r * row_b * 2));
           }
         }
 #pragma unroll
@@ -562,110 +688,228 @@ field_fused2_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ 
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < BIN; ++r) m[r] = ldg128_stream(rp + r * W, pol_stream);
+        for (int r = 0; r < BIN; ++r) m[r] = ldg128_stream(rp + r * row_b, pol_stream);
         if (HAS_ILLUM) {
-          const float* ip = illum + (size_t)c * plane + off;
 #pragma unroll
           for (int r = 0; r < BIN; ++r) {
-            il[r][0] = ldg128_keep(ip + r * W, pol_keep);
-            il[r][1] = ldg128_keep(ip + r * W + 4, pol_keep);
+            il[r][0] = ldg128_keep(ip + r * row_b * 2, pol_keep);
+            il[r][1] = ldg128_keep(ip + r * row_b * 2 + 16, pol_keep);
           }
         }
         for (int z = 1; z < nz; ++z) {
 #pragma unroll
           for (int r = 0; r < BIN; ++r)
-            m[r] = vmax_u16x8(m[r], ldg128_stream(rp + (size_t)z * plane + r * W, pol_stream));
+            m[r] = vmax_u16x8(m[r], ldg128_stream(rp + (size_t)z * plane_b + r * row_b, pol_stream));
+        }
+        if (c + 1 < C) {
+          const char* np = rp + chan_b;
+          for (int z = 0; z < nz; ++z)
+#pragma unroll
+            for (int r = 0; r < BIN; ++r)
+              if (pf_raw) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + (size_t)z * plane_b + r * row_b));
+          if (HAS_ILLUM) {
+            const char* nip = ip + (size_t)plane_b * 2;
+#pragma unroll
+            for (int r = 0; r < BIN; ++r)
+              if (pf_ill) asm volatile("prefetch.global.L2 [%0];" ::"l"(nip + r * row_b * 2));
+          }
         }
       }
-      if (maxproj != nullptr) {
-        uint16_t* mp = maxproj + fc * plane + off;
+      const size_t fc = (size_t)f * C + c;
+      if (maxproj != nullptr && col_ok) {
+        char* mp = reinterpret_cast<char*>(maxproj) + fc * plane_b + (size_t)off * 2;
 #pragma unroll
-        for (int r = 0; r < BIN; ++r) stg128_stream(mp + r * W, m[r], pol_stream);
+        for (int r = 0; r < BIN; ++r) stg128_stream(mp + r * row_b, m[r], pol_stream);
       }
+      f2_consume<BIN, HAS_ILLUM>(m, il, illum_is_rcp, binned != nullptr && col_ok,
+                                 reinterpret_cast<char*>(binned) + fc * bplane_b + boff, pol_stream, L, warp_fg, c, sh,
+                                 rec_f, C, lab);
+      rp += chan_b;
+      ip += (size_t)plane_b * 2;
     }
+  }
+  if (overflow) atomicOr(flags + f, 1);
+  oa_finish<HAS_ILLUM>(sh, rec_f, C);
+}
 
-    if (HAS_ILLUM) {
-      u64 q[BIN][F2_WPR];
+// ---- kernel B: rows staged in shared memory by the TMA unit ---------------------------------------------
+// Same tiling, same arithmetic; the difference is how a channel's rows reach the lanes.  Every warp
+// owns one stage in shared memory (Z x BIN raw rows + BIN function rows of its 256-column span).  The
+// lanes read a channel's rows out of the stage at the top of the channel (LDS.128, immediate offsets);
+// right after that one elected lane hands the rows of channel c + 1 to the TMA unit (cp.async.bulk,
+// mbarrier complete_tx), so a whole channel of arithmetic covers the HBM latency of the next one.  No
+// registers are tied up by loads in flight (the direct kernel holds 40 of its 64 registers for them),
+// no per-lane address arithmetic is needed for inputs, and occupancy no longer has to hide memory
+// latency.
+constexpr int F2S_CAP = 48;                       // records per CTA (overflowing run heads flush directly)
+typedef OaSharedT<F2S_CAP> F2sShared;
+
+__device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f2_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void f2_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f2_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(f2_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void f2_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar,
+                                             uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(f2_smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ uint4 f2_lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+constexpr int F2S_RAW_ROW = 32 * OA_PX * 2;       // bytes of a warp's span of one uint16 row (512)
+constexpr int F2S_ILL_ROW = 32 * OA_PX * 4;       // ... of one float32 row (1024)
+__host__ __device__ constexpr size_t f2s_stage_bytes(int bin, int nz, bool has_illum) {
+  return (size_t)bin * ((size_t)nz * F2S_RAW_ROW + (has_illum ? F2S_ILL_ROW : 0));
+}
+__host__ __device__ constexpr size_t f2s_records_bytes() { return (sizeof(F2sShared) + 127) / 128 * 128; }
+static size_t f2s_smem_bytes(int bin, int nz, bool has_illum) {
+  return f2s_records_bytes() + (size_t)OA_WARPS * f2s_stage_bytes(bin, nz, has_illum) + OA_WARPS * sizeof(uint64_t);
+}
+__device__ __forceinline__ bool f2_elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(e));
+  return e != 0u;
+}
+
+template <int BIN, int ZT, bool HAS_ILLUM>
+__global__ void __launch_bounds__(OA_THREADS, BIN == 4 ? 3 : 6)
+field_fused2s_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ illum, int illum_is_rcp,
+                     const void* __restrict__ labels, int label_bytes, uint16_t* __restrict__ maxproj,
+                     void* __restrict__ binned, unsigned long long* __restrict__ rec, int* __restrict__ flags,
+                     int Nmax, int C, int Z, int H, int W) {
+  extern __shared__ __align__(128) unsigned char f2s_smem[];
+  F2sShared& sh = *reinterpret_cast<F2sShared*>(f2s_smem);
+  const int nz = ZT > 0 ? ZT : Z;
+  const uint32_t stage_b = (uint32_t)f2s_stage_bytes(BIN, nz, HAS_ILLUM);
+  // the shuffle tells the compiler the warp index is warp-uniform: everything the TMA issue needs
+  // (stage address, row pointers, byte counts) then lives in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  unsigned char* ring = f2s_smem + f2s_records_bytes() + (size_t)warp * stage_b;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(f2s_smem + f2s_records_bytes() + (size_t)OA_WARPS * stage_b) + warp;
+  if (lane == 0) {
+    f2_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  oa_init_shared(sh);                            // __syncthreads inside
+  const int f = blockIdx.x, tile_x = blockIdx.y, tile_y = blockIdx.z;
+  const int rb = tile_y * OA_WARPS + warp;
+  const int y0 = rb * BIN;
+  const int xw0 = tile_x * 32 * OA_PX;
+  const int g = tile_x * 32 + lane;
+  const int x0 = g * OA_PX;
+  unsigned long long* rec_f = rec + (size_t)f * Nmax * k3_record_words(C);
+  bool overflow = false;
+  if (y0 < H) {
+    const bool col_ok = x0 < W;
+    const unsigned plane = (unsigned)H * (unsigned)W;
+    const unsigned row_b = (unsigned)W * 2u, plane_b = plane * 2u;
+    const unsigned woff = (unsigned)y0 * (unsigned)W + (unsigned)xw0;          // the warp's first pixel
+    const unsigned off = (unsigned)y0 * (unsigned)W + (unsigned)(col_ok ? x0 : W - OA_PX);
+    const uint32_t raw_n = (uint32_t)min(32 * OA_PX, W - xw0) * 2u;             // bytes of the warp's span inside the image
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_keep = policy_evict_last();
+    const char* wrp = reinterpret_cast<const char*>(raw) + (size_t)f * C * nz * plane_b + (size_t)woff * 2;
+    const char* wip = reinterpret_cast<const char*>(illum) + (size_t)woff * 4;
+    const size_t chan_b = (size_t)nz * plane_b;
+    const uint32_t ring_s = f2_smem_u32(ring);
+
+    // one elected lane hands the rows of the next channel to the TMA unit; the mbarrier counts the bytes
+    const char* nrp = wrp;                       // rows of the next channel to issue (uniform, walks by chan_b)
+    const char* nip = wip;
+    const uint32_t tx_bytes = (uint32_t)BIN * ((uint32_t)nz * raw_n + (HAS_ILLUM ? 2u * raw_n : 0u));
+    auto issue = [&]() {
+      if (f2_elect_one()) {
+        f2_mbar_expect_tx(bar, tx_bytes);
+        const char* rp = nrp;
+        uint32_t dst = ring_s;
+        for (int z = 0; z < nz; ++z) {
+#pragma unroll
+          for (int r = 0; r < BIN; ++r) f2_bulk_load(dst + (uint32_t)r * F2S_RAW_ROW, rp + r * row_b, raw_n, bar, pol_stream);
+          rp += plane_b;
+          dst += (uint32_t)BIN * F2S_RAW_ROW;
+        }
+        if (HAS_ILLUM) {
+#pragma unroll
+          for (int r = 0; r < BIN; ++r) f2_bulk_load(dst + (uint32_t)r * F2S_ILL_ROW, nip + r * row_b * 2, 2u * raw_n, bar, pol_keep);
+        }
+      }
+      nrp += chan_b;
+      nip += (size_t)plane_b * 2;
+    };
+    issue();
+
+    F2Labels lab;
+    lab.base = labels; lab.elem = (size_t)f * plane + off; lab.label_bytes = label_bytes; lab.W = W;
+    unsigned lw[BIN][F2_WPR];
+    f2_load_labels<BIN>(lw, reinterpret_cast<const char*>(labels) + lab.elem * (size_t)label_bytes, label_bytes, row_b,
+                        Nmax, col_ok, pol_stream, overflow);
+    F2Lane<BIN> L;
+    L.lane = lane;
+    unsigned wany = 0u;
+#pragma unroll
+    for (int r = 0; r < BIN; ++r)
+#pragma unroll
+      for (int k = 0; k < F2_WPR; ++k) wany |= lw[r][k];
+    const bool warp_fg = __any_sync(OA_FULL, wany != 0u);
+    if (warp_fg) f2_begin<BIN>(L, lw, (unsigned)Nmax, y0, xw0, sh, rec_f, C, overflow);
+
+    constexpr int NB = OA_PX / BIN;
+    const unsigned bplane_b = (plane / (BIN * BIN)) * 4u;
+    const unsigned boff = ((unsigned)rb * (unsigned)(W / BIN) + (unsigned)g * NB) * 4u;
+    const uint32_t lane_raw = (uint32_t)lane * 16u, lane_ill = (uint32_t)lane * 32u;
+    for (int c = 0; c < C; ++c) {
+      f2_mbar_wait(bar, (uint32_t)c & 1u);
+      const uint32_t st = ring_s;
+      uint4 m[BIN];
+      uint4 il[BIN][2];
 #pragma unroll
       for (int r = 0; r < BIN; ++r) {
-        const unsigned mw[4] = {m[r].x, m[r].y, m[r].z, m[r].w};
-        unsigned rc[8] = {il[r][0].x, il[r][0].y, il[r][0].z, il[r][0].w, il[r][1].x, il[r][1].y, il[r][1].z, il[r][1].w};
-        if (!illum_is_rcp) {
+        m[r] = f2_lds128(st + (uint32_t)r * F2S_RAW_ROW + lane_raw);
+        if (ZT > 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rc[i] = __float_as_uint(rcp_approx(__uint_as_float(rc[i])));
+          for (int z = 1; z < ZT; ++z) m[r] = vmax_u16x8(m[r], f2_lds128(st + (uint32_t)(z * BIN + r) * F2S_RAW_ROW + lane_raw));
+        } else {
+          for (int z = 1; z < nz; ++z) m[r] = vmax_u16x8(m[r], f2_lds128(st + (uint32_t)(z * BIN + r) * F2S_RAW_ROW + lane_raw));
         }
-#pragma unroll
-        for (int k = 0; k < F2_WPR; ++k) {
-          // 2^23 + v as float bits, then - 2^23: exact uint16 -> float without I2F
-          const u64 fl = pk2u(__byte_perm(mw[k], 0x4b000000u, 0x7610), __byte_perm(mw[k], 0x4b000000u, 0x7632));
-          q[r][k] = mul2(add2(fl, NMAGIC2), pk2u(rc[2 * k], rc[2 * k + 1]));
+        if (HAS_ILLUM) {
+          const uint32_t ia = st + (uint32_t)(nz * BIN) * F2S_RAW_ROW + (uint32_t)r * F2S_ILL_ROW + lane_ill;
+          il[r][0] = f2_lds128(ia);
+          il[r][1] = f2_lds128(ia + 16u);
         }
       }
-      if (active && binned != nullptr) {
-        float bs[NB];
-        if (BIN == 1) {
-#pragma unroll
-          for (int k = 0; k < F2_WPR; ++k) upk2(q[0][k], bs[(2 * k) % NB], bs[(2 * k + 1) % NB]);
-        } else {
-          u64 vs[F2_WPR];
-#pragma unroll
-          for (int k = 0; k < F2_WPR; ++k) {
-            vs[k] = q[0][k];
-#pragma unroll
-            for (int r = 1; r < BIN; ++r) vs[k] = add2(vs[k], q[r][k]);
-          }
-          float h[F2_WPR];
-#pragma unroll
-          for (int k = 0; k < F2_WPR; ++k) {
-            float a, b;
-            upk2(vs[k], a, b);
-            h[k] = a + b;
-          }
-          if (BIN == 2) {
-#pragma unroll
-            for (int k = 0; k < F2_WPR; ++k) bs[k % NB] = h[k];
-          } else {
-            bs[0] = h[0] + h[1];
-            bs[1 % NB] = h[2] + h[3];
-          }
-        }
-        float* bp = reinterpret_cast<float*>(binned) + fc * (plane / (BIN * BIN)) + (size_t)rb * (W / BIN) + (size_t)g * NB;
-        if (NB == 8) {
-          stg128_stream(bp, make_uint4(__float_as_uint(bs[0]), __float_as_uint(bs[1 % NB]), __float_as_uint(bs[2 % NB]),
-                                       __float_as_uint(bs[3 % NB])), pol_stream);
-          stg128_stream(bp + 4, make_uint4(__float_as_uint(bs[4 % NB]), __float_as_uint(bs[5 % NB]),
-                                           __float_as_uint(bs[6 % NB]), __float_as_uint(bs[7 % NB])), pol_stream);
-        } else if (NB == 4) {
-          stg128_stream(bp, make_uint4(__float_as_uint(bs[0]), __float_as_uint(bs[1 % NB]), __float_as_uint(bs[2 % NB]),
-                                       __float_as_uint(bs[3 % NB])), pol_stream);
-        } else {
-          stg64_stream(bp, make_uint2(__float_as_uint(bs[0]), __float_as_uint(bs[1 % NB])), pol_stream);
-        }
+      if (c + 1 < C) {
+        __syncwarp();                            // every lane has its rows in registers: the stage is free
+        issue();
       }
-      if (warp_fg) f2_channel_float<BIN>(L, c, q, sh, rec_f, C, lab_lane, label_bytes, W);
-    } else {
-      unsigned iv[BIN][OA_PX];
+      const size_t fc = (size_t)f * C + c;
+      if (maxproj != nullptr && col_ok) {
+        char* mp = reinterpret_cast<char*>(maxproj) + fc * plane_b + (size_t)off * 2;
 #pragma unroll
-      for (int r = 0; r < BIN; ++r) unpack_u16x8(m[r], iv[r]);
-      if (active && binned != nullptr) {
-        unsigned bs[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) bs[j] = 0u;
-#pragma unroll
-        for (int r = 0; r < BIN; ++r)
-#pragma unroll
-          for (int i = 0; i < OA_PX; ++i) bs[i / BIN] += iv[r][i];
-        unsigned* bp = reinterpret_cast<unsigned*>(binned) + fc * (plane / (BIN * BIN)) + (size_t)rb * (W / BIN) + (size_t)g * NB;
-        if (NB == 8) {
-          stg128_stream(bp, make_uint4(bs[0], bs[1 % NB], bs[2 % NB], bs[3 % NB]), pol_stream);
-          stg128_stream(bp + 4, make_uint4(bs[4 % NB], bs[5 % NB], bs[6 % NB], bs[7 % NB]), pol_stream);
-        } else if (NB == 4) {
-          stg128_stream(bp, make_uint4(bs[0], bs[1 % NB], bs[2 % NB], bs[3 % NB]), pol_stream);
-        } else {
-          stg64_stream(bp, make_uint2(bs[0], bs[1 % NB]), pol_stream);
-        }
+        for (int r = 0; r < BIN; ++r) stg128_stream(mp + r * row_b, m[r], pol_stream);
       }
-      if (warp_fg) f2_channel_int<BIN>(L, c, iv, sh, rec_f, C, lab_lane, label_bytes, W);
+      f2_consume<BIN, HAS_ILLUM>(m, il, illum_is_rcp, binned != nullptr && col_ok,
+                                 reinterpret_cast<char*>(binned) + fc * bplane_b + boff, pol_stream, L, warp_fg, c, sh,
+                                 rec_f, C, lab);
     }
   }
   if (overflow) atomicOr(flags + f, 1);
@@ -678,20 +922,45 @@ illum_reciprocal_kernel(const float* __restrict__ in, float* __restrict__ out, s
   if (i < n) out[i] = __frcp_rn(in[i]);
 }
 
+static bool use_staged_kernel() {
+  static const bool v = [] {
+    const char* e = getenv("IPS_FUSED_STAGED");      // 1 = TMA-staged kernel, 0 = direct loads (A/B measurements)
+    return e == nullptr ? true : e[0] != '0';
+  }();
+  return v;
+}
+
 template <int BIN, bool HAS_ILLUM>
-static void launch_fused2(int Z, int grid, cudaStream_t st, const uint16_t* raw, const float* illum, int is_rcp,
-                          const void* labels, int label_bytes, uint16_t* maxproj, void* binned,
-                          unsigned long long* rec, int* flags, int Nmax, int F, int C, int H, int W, int tiles_x) {
-#define IPS_F2_CASE(ZT)                                                                                      \
-  field_fused2_kernel<BIN, ZT, HAS_ILLUM><<<grid, OA_THREADS, 0, st>>>(raw, illum, is_rcp, labels, label_bytes, \
-                                                                        maxproj, binned, rec, flags, Nmax, F, C, \
-                                                                        Z, H, W, tiles_x)
+static int launch_fused2(int Z, dim3 grid, cudaStream_t st, const uint16_t* raw, const float* illum, int is_rcp,
+                         const void* labels, int label_bytes, uint16_t* maxproj, void* binned,
+                         unsigned long long* rec, int* flags, int Nmax, int C, int H, int W) {
+  const size_t smem = f2s_smem_bytes(BIN, Z, HAS_ILLUM);
+  const bool staged = use_staged_kernel() && smem <= 200 * 1024;
+#define IPS_F2_CASE(ZT)                                                                                           \
+  do {                                                                                                            \
+    if (staged) {                                                                                                 \
+      static size_t attr_smem = 0;     /* one device per process (one rank per GPU) */                            \
+      if (smem > attr_smem) {                                                                                     \
+        IPS_CUDA_OK(cudaFuncSetAttribute(field_fused2s_kernel<BIN, ZT, HAS_ILLUM>,                                \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+        IPS_CUDA_OK(cudaFuncSetAttribute(field_fused2s_kernel<BIN, ZT, HAS_ILLUM>,                                \
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, 100));                   \
+        attr_smem = smem;                                                                                         \
+      }                                                                                                           \
+      field_fused2s_kernel<BIN, ZT, HAS_ILLUM><<<grid, OA_THREADS, smem, st>>>(raw, illum, is_rcp, labels, label_bytes, \
+                                                                               maxproj, binned, rec, flags, Nmax, C, Z, H, W); \
+    } else {                                                                                                      \
+      field_fused2_kernel<BIN, ZT, HAS_ILLUM><<<grid, OA_THREADS, 0, st>>>(raw, illum, is_rcp, labels, label_bytes, \
+                                                                           maxproj, binned, rec, flags, Nmax, C, Z, H, W); \
+    }                                                                                                             \
+  } while (0)
   switch (Z) {
     case 3: IPS_F2_CASE(3); break;
     case 5: IPS_F2_CASE(5); break;
     default: IPS_F2_CASE(0); break;
   }
 #undef IPS_F2_CASE
+  return IPS_OK;
 }
 
 // defined in object_stats.cu
@@ -715,19 +984,19 @@ int field_fused2_try(const uint16_t* raw, const float* illum, int illum_is_rcp, 
   if (rc != IPS_OK) return rc;
   const int tiles_x = (W + 32 * OA_PX - 1) / (32 * OA_PX);
   const int tiles_y = (H / bin + OA_WARPS - 1) / OA_WARPS;
-  const long blocks_l = (long)tiles_x * tiles_y * F;
-  if (blocks_l > 0x7fffffffL) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_field_fused: batch too large for one launch");
-  const int grid = (int)blocks_l;
+  if (tiles_x > 65535 || tiles_y > 65535) return 0;
+  const dim3 grid((unsigned)F, (unsigned)tiles_x, (unsigned)tiles_y);
   const bool has_illum = illum != nullptr;
 #define IPS_F2_BIN(B)                                                                                              \
   do {                                                                                                             \
-    if (has_illum) launch_fused2<B, true>(Z, grid, st, raw, illum, illum_is_rcp, labels, label_bytes, maxproj, binned, rec, flags, Nmax, F, C, H, W, tiles_x); \
-    else launch_fused2<B, false>(Z, grid, st, raw, illum, 0, labels, label_bytes, maxproj, binned, rec, flags, Nmax, F, C, H, W, tiles_x); \
+    if (has_illum) rc = launch_fused2<B, true>(Z, grid, st, raw, illum, illum_is_rcp, labels, label_bytes, maxproj, binned, rec, flags, Nmax, C, H, W); \
+    else rc = launch_fused2<B, false>(Z, grid, st, raw, illum, 0, labels, label_bytes, maxproj, binned, rec, flags, Nmax, C, H, W); \
   } while (0)
   if (bin == 1) IPS_F2_BIN(1);
   else if (bin == 2) IPS_F2_BIN(2);
   else IPS_F2_BIN(4);
 #undef IPS_F2_BIN
+  if (rc != IPS_OK) return rc;
   IPS_LAUNCH_OK("field_fused2_kernel");
   rc = k3_launch_compact(rec, flags, n_objects, ints, flts, Nmax, F, C, intensity_scale, has_illum, st);
   return rc == IPS_OK ? 1 : rc;

@@ -43,15 +43,18 @@ struct OaGeom {
   int ymin, ymax1, xmin, xmax1;
 };
 
-struct OaShared {
+template <int CAP_>
+struct OaSharedT {
+  static constexpr int CAP = CAP_;
   int count;
   int n_owner;
-  int label[OA_CAP];
-  int owner[OA_CAP];
-  OaGeom geom[OA_CAP];
-  unsigned long long s1[OA_CAP][OA_CMAX], s2[OA_CAP][OA_CMAX];   // float64 bits or uint64
-  unsigned mn[OA_CAP][OA_CMAX], mx[OA_CAP][OA_CMAX];             // float bits or integers
+  int label[CAP_];
+  int owner[CAP_];
+  OaGeom geom[CAP_];
+  unsigned long long s1[CAP_][OA_CMAX], s2[CAP_][OA_CMAX];   // float64 bits or uint64
+  unsigned mn[CAP_][OA_CMAX], mx[CAP_][OA_CMAX];             // float bits or integers
 };
+typedef OaSharedT<OA_CAP> OaShared;
 
 // ---- global flushes -----------------------------------------------------------------------
 __device__ __forceinline__ void oa_flush_geom(unsigned long long* __restrict__ rec_f, int C, int label,
@@ -395,17 +398,18 @@ __device__ __forceinline__ void oa_channel(const OaLane<ROWS>& L, int c, const f
   }
 }
 
-__device__ __forceinline__ void oa_init_shared(OaShared& sh) {
+template <typename SH>
+__device__ __forceinline__ void oa_init_shared(SH& sh) {
   if (threadIdx.x == 0) { sh.count = 0; sh.n_owner = 0; }
   __syncthreads();
 }
 
 // After every lane of the CTA has folded all channels: merge records of equal label and flush
 // each distinct label of the tile once.
-template <bool FLOAT_MODE>
-__device__ __forceinline__ void oa_finish(OaShared& sh, unsigned long long* __restrict__ rec_f, int C) {
+template <bool FLOAT_MODE, typename SH>
+__device__ __forceinline__ void oa_finish(SH& sh, unsigned long long* __restrict__ rec_f, int C) {
   __syncthreads();
-  const int n = min(sh.count, OA_CAP);
+  const int n = min(sh.count, SH::CAP);
   for (int r = threadIdx.x; r < n; r += OA_THREADS) {
     const int lab = sh.label[r];
     bool own = true;
