@@ -52,6 +52,10 @@ PROTOTYPES = {
     "ips_lanczos_workspace_bytes": (sz, [i, i, i, i, i]),
     "ips_lanczos_resize_u16": (i, [p, p, i, i, i, i, i, p, sz, p]),
     "ips_ring_sums": (i, [p, p, p, i, i, i, i, p]),
+    "ips_rps_prepare_workspace_bytes": (sz, [i64]),
+    "ips_rps_prepare": (i, [p, p, p, p, p, i64, p, sz, p]),
+    "ips_ring_sums_half": (i, [p, p, p, i, i, i, i, p]),
+    "ips_loglog_slope": (i, [p, p, i, i, p]),
     "ips_cosine_workspace_bytes": (sz, [i, i]),
     "ips_cosine_triu": (i, [p, p, i, p, p, i, i, p, sz, p]),
     "ips_cosine_pairs_workspace_bytes": (sz, [i, i]),

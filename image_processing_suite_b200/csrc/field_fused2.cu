@@ -792,7 +792,7 @@ __device__ __forceinline__ bool f2_elect_one() {
 }
 
 template <int BIN, int ZT, bool HAS_ILLUM>
-__global__ void __launch_bounds__(OA_THREADS, BIN == 4 ? 3 : 6)
+__global__ void __launch_bounds__(OA_THREADS, BIN == 4 ? 3 : 7)
 field_fused2s_kernel(const uint16_t* __restrict__ raw, const float* __restrict__ illum, int illum_is_rcp,
                      const void* __restrict__ labels, int label_bytes, uint16_t* __restrict__ maxproj,
                      void* __restrict__ binned, unsigned long long* __restrict__ rec, int* __restrict__ flags,

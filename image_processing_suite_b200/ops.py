@@ -261,6 +261,57 @@ def ring_sums(spec, n_rings):
     return mag, pw
 
 
+def rps_spectrum(image, illum=None, want_corrected=False):
+    """rps() of Illumination_QC_mult.py:31-70 up to the ring sums, on the device: image [H][W]
+    uint16 or float64, illum [H][W] float64 or None (the float64 divide of :145-150).
+    Returns (mag [n_rings], pow [n_rings]) float64 device tensors for ring labels 2 .. n_rings + 1
+    (empty when min(H, W) < 24), plus the float64 corrected image when ``want_corrected``.
+    Median by exact radix select, real FFT (cuFFT via torch.fft.rfft2 is the FFT library), ring
+    sums over the Hermitian half -- no host round trip."""
+    if not isinstance(image, torch.Tensor) or image.dtype not in (torch.uint16, torch.float64):
+        raise TypeError("image must be a uint16 or float64 tensor")
+    _check(image, "image", image.dtype, 2)
+    dev = image.device
+    H, W = image.shape
+    if illum is not None:
+        _check(illum, "illum", torch.float64, 2, dev)
+        if tuple(illum.shape) != (H, W):
+            raise ValueError("illum shape mismatch")
+    import math
+    n_rings = max(int(math.floor(min(H, W) / 8.0)) - 2, 0)
+    with torch.cuda.device(dev):
+        z = torch.empty((H, W), dtype=torch.float64, device=dev)
+        computed = image.dtype == torch.uint16 or illum is not None
+        corrected = torch.empty((H, W), dtype=torch.float64, device=dev) if (computed and want_corrected) else (z if computed else None)
+        ws = _workspace(capi.call("ips_rps_prepare_workspace_bytes", H * W), dev)
+        capi.call("ips_rps_prepare", _ptr(image) if image.dtype == torch.uint16 else None,
+                  _ptr(image) if image.dtype == torch.float64 else None, _ptr(illum), _ptr(corrected), _ptr(z), H * W,
+                  _ptr(ws), ws.numel(), _stream(dev))
+        mag = torch.empty((n_rings,), dtype=torch.float64, device=dev)
+        pw = torch.empty((n_rings,), dtype=torch.float64, device=dev)
+        if n_rings > 0:
+            spec = torch.fft.rfft2(z).contiguous()         # cuFFT's two-pass result can come back strided
+            capi.call("ips_ring_sums_half", _ptr(spec), _ptr(mag), _ptr(pw), n_rings, 1, H, W, _stream(dev))
+    if want_corrected:
+        return mag, pw, (corrected if computed else image)
+    return mag, pw
+
+
+def loglog_slope(powersum):
+    """Least-squares slope of log(power) over log(ring label) (labels 2..), rings with power > 0,
+    0.0 with fewer than three (Illumination_QC_mult.py:108-114).  powersum [F][n_rings] or
+    [n_rings] float64 (device) -> float64 device tensor [F]."""
+    _check(powersum, "powersum", torch.float64)
+    p2 = powersum.reshape(-1, powersum.shape[-1])
+    dev = powersum.device
+    F, n = p2.shape
+    with torch.cuda.device(dev):
+        out = torch.zeros((F,), dtype=torch.float64, device=dev)
+        if n > 0 and F > 0:
+            capi.call("ips_loglog_slope", _ptr(p2.contiguous()), _ptr(out), n, F, _stream(dev))
+    return out
+
+
 # ---- well aggregation -------------------------------------------------------------------
 def well_mean(rows, well, n_wells):
     """Per-well mean of object rows [N][D] float32 with well ids [N] int32 in [0, n_wells).

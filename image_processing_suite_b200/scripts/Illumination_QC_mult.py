@@ -2,9 +2,11 @@
 
 Per site x channel: read the TIFF, divide by the pre-loaded illumination function
 (Illumination_QC_mult.py:145-150), ImageQuality_PowerLogLogSlope (rps, :31-70, :104-116) and
-ImageQuality_PercentMaximal (:73-95).  On the device: the divide and the spectrum are float64
-(torch.fft is the FFT library, as scipy.fftpack is in the reference), the ring-keyed sums are
-ips_ring_sums, PercentMaximal is the float64 side reduction of ips_preprocess_fused.
+ImageQuality_PercentMaximal (:73-95).  On the device, one stream, one device -> host read per
+channel: float64 divide + mean + exact radix-select median (ips_rps_prepare), real FFT (cuFFT via
+torch.fft.rfft2 is the FFT library, as scipy.fftpack is in the reference), ring-keyed sums over
+the Hermitian half (ips_ring_sums_half), log-log least squares (ips_loglog_slope); PercentMaximal
+is the float64 side reduction of ips_preprocess_fused.
 Error convention unchanged: process_site never raises; failures become QC_Error_{ch} strings.
 """
 import argparse
@@ -52,22 +54,18 @@ def _to_device_f64(image):
 def rps(img):
     """Radial power spectrum ring sums, Illumination_QC_mult.py:31-70.
     Returns (labels, magsum, powersum) as NumPy arrays, or the reference's degenerate
-    ``[2], [0], [0]`` lists when min(H, W) < 24 (no ring to sum, :70)."""
-    import torch
+    ``[2], [0], [0]`` lists when min(H, W) < 24 (no ring to sum, :70).
+    On the device end to end: exact radix-select median, real FFT, ring sums over the Hermitian
+    half (ops.rps_spectrum)."""
     from .. import ops
     x = _to_device_f64(img)
     assert x.dim() == 2
     H, W = x.shape
-    maxwidth = min(H, W) / 8.0
-    if float(x.max() - x.min()) > 0:                         # np.ptp(img) > 0  (:52)
-        dev_abs = (x - x.mean()).abs().flatten()
-        x = x / torch.quantile(dev_abs, 0.5, interpolation="midpoint")   # np.median
-    spec = torch.fft.fft2(x - x.mean())                      # unshifted, DC removed (:57)
-    labels = np.arange(2, np.floor(maxwidth)).astype(int)
+    labels = np.arange(2, np.floor(min(H, W) / 8.0)).astype(int)
     if len(labels) == 0:
         return [2], [0], [0]
-    mag, pw = ops.ring_sums(spec[None].contiguous(), len(labels))
-    return labels, mag[0].cpu().numpy(), pw[0].cpu().numpy()
+    mag, pw = ops.rps_spectrum(x.contiguous())
+    return labels, mag.cpu().numpy(), pw.cpu().numpy()
 
 
 def calculate_saturation_cp_exact(image, mask=None):
@@ -132,23 +130,35 @@ def _illum_on_device(illum):
     return d64, d32
 
 
-def _corrected_and_pct(img_u16, illum):
-    """(float64 corrected image on the device, PercentMaximal).  When the illumination
-    function is float32-exact the fused kernel computes the divide-side PercentMaximal."""
+def _channel_metrics(img_u16, illum):
+    """(PowerLogLogSlope, PercentMaximal) of one uint16 channel image on the device, as device /
+    host scalars resolved with ONE synchronisation: the float64 divide, the exact median, the
+    real FFT, the ring sums and the log-log regression all stay on the stream (ops.rps_spectrum,
+    ops.loglog_slope); PercentMaximal is the float64 side reduction of the fused kernel when the
+    function is float32-exact, else an equality count on the float64 corrected image."""
     import torch
     from .. import ops
     raw = img_u16 if isinstance(img_u16, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img_u16)).cuda()
-    if illum is None or tuple(img_u16.shape) != tuple(illum.shape):        # silently uncorrected (:148-153)
-        r = ops.preprocess_fused(raw[None, None, None], None, bin=1, want_maxproj=False, want_binned=False,
-                                 want_pct_maximal=True)
-        return raw.to(torch.float64), float(r["pct_maximal"][0, 0].item())
-    d64, d32 = _illum_on_device(illum)
-    corrected = raw.to(torch.float64) / d64
-    if d32 is not None:
-        r = ops.preprocess_fused(raw[None, None, None], d32, bin=1, want_maxproj=False, want_binned=False,
-                                 want_pct_maximal=True)
-        return corrected, float(r["pct_maximal"][0, 0].item())
-    return corrected, calculate_saturation_cp_exact(corrected)
+    raw = raw.contiguous()
+    d64 = d32 = None
+    if illum is not None and tuple(img_u16.shape) == tuple(illum.shape):      # else silently uncorrected (:148-153)
+        d64, d32 = _illum_on_device(illum)
+    need_corrected = d64 is not None and d32 is None
+    out = ops.rps_spectrum(raw, d64, want_corrected=need_corrected)
+    pw = out[1]
+    slope = ops.loglog_slope(pw) if pw.numel() else None             # no ring at all: the reference's NaN (:70, :115)
+    nan = torch.full((), float("nan"), dtype=torch.float64, device=raw.device)
+    if need_corrected:
+        corrected = out[2]
+        count = (corrected == corrected.max()).sum().to(torch.float64)
+        got = torch.stack([slope[0] if slope is not None else nan, count]).tolist()      # the one device -> host read
+        # the reference's own expression, evaluated on the host (:93; a device divide by a scalar may
+        # be a multiply by its reciprocal)
+        return got[0], 100.0 * float(got[1]) / float(corrected.numel())
+    r = ops.preprocess_fused(raw[None, None, None], d32, bin=1, want_maxproj=False, want_binned=False,
+                             want_pct_maximal=True)
+    got = torch.stack([slope[0] if slope is not None else nan, r["pct_maximal"][0, 0]]).tolist()
+    return got[0], got[1]
 
 
 def process_site(site_data):
@@ -171,12 +181,11 @@ def process_site(site_data):
                     img = tiffio.decode(data)
                 illum = illum_cache[i] if illum_cache and illum_cache[i] is not None else None
                 if isinstance(img, torch.Tensor) or (img.dtype == np.uint16 and img.ndim == 2):
-                    corrected, pct = _corrected_and_pct(img, illum)
                     try:
-                        radii, _, powersum = rps(corrected)
-                        site_results[f'ImageQuality_PowerLogLogSlope_{ch_name}'] = _slope(radii, powersum)
+                        slope, pct = _channel_metrics(img, illum)
                     except Exception:
-                        site_results[f'ImageQuality_PowerLogLogSlope_{ch_name}'] = np.nan
+                        slope = pct = np.nan
+                    site_results[f'ImageQuality_PowerLogLogSlope_{ch_name}'] = slope
                     site_results[f'ImageQuality_PercentMaximal_{ch_name}'] = pct
                 else:
                     x = img.astype(float)

@@ -166,6 +166,23 @@ int ips_lanczos_resize_u16(const uint16_t* in, uint16_t* out, int C, int H, int 
 int ips_ring_sums(const double* spec_interleaved, double* mag_out, double* pow_out, int n_rings,
                   int F, int H, int W, ips_stream_t stream);
 
+/* The same metric without host round trips (one image per call; see csrc/qc.cu):
+ * ips_rps_prepare     exactly one of raw_u16 / img_f64 [n]; illum_f64 [n] or NULL (the float64 divide of
+ *                     Illumination_QC_mult.py:145-150).  corrected_out [n] float64 receives the (divided)
+ *                     image when one is computed here (uint16 input or a division; may alias fft_in_out).
+ *                     fft_in_out [n] = img / median(|img - mean|) - its mean (:52-57; img - mean for a
+ *                     constant image): the input of the real FFT.  Median: exact radix select.
+ * ips_ring_sums_half  as ips_ring_sums on the Hermitian half [F][H][W/2+1][2] of a real FFT.
+ * ips_loglog_slope    powersum [F][n_rings] -> slope_out [F]: least squares of log(power) over
+ *                     log(label), labels 2.., rings with power > 0; 0.0 with fewer than three (:108-114). */
+size_t ips_rps_prepare_workspace_bytes(int64_t n);
+int ips_rps_prepare(const uint16_t* raw_u16, const double* img_f64, const double* illum_f64,
+                    double* corrected_out, double* fft_in_out, int64_t n, void* ws, size_t ws_bytes,
+                    ips_stream_t stream);
+int ips_ring_sums_half(const double* half_spec_interleaved, double* mag_out, double* pow_out,
+                       int n_rings, int F, int H, int W, ips_stream_t stream);
+int ips_loglog_slope(const double* powersum, double* slope_out, int n_rings, int F, ips_stream_t stream);
+
 /* ---- K4: replicate-group cosine similarity, strict upper triangle ---------------------
  * Replaces  cosine_similarity(features) -> triu(k=1) -> mean
  *           Feature_select_cosine_ami.py:145-149, Pycyto_pertime.py:132-140

@@ -160,3 +160,54 @@ def test_header_blocks_pack_count_and_aggregate():
     mean_r, count_r = ops.well_mean(rows, ids, 10)
     np.testing.assert_array_equal(host(mean_b).view(np.int64), host(mean_r).view(np.int64))
     np.testing.assert_array_equal(host(count_b), host(count_r))
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (96, 81), (45, 130), (216, 216), (250, 333)])
+@pytest.mark.parametrize("kind", ["float64", "uint16", "uint16/illum"])
+def test_rps_on_device_matches_reference_arithmetic(hw, kind):
+    """ops.rps_spectrum + ops.loglog_slope (exact radix-select median, real FFT, ring sums over the
+    Hermitian half, device least squares) vs the oracle's rps / slope (Illumination_QC_mult.py:31-116)."""
+    require_gpu()
+    import torch
+    from image_processing_suite_b200 import ops
+    rng = np.random.default_rng(hash((hw, kind)) % 2 ** 31)
+    H, W = hw
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = 2000.0 + 900.0 * np.sin(yy / 7.0) * np.cos(xx / 5.0) + rng.normal(0, 60.0, hw)
+    if kind == "float64":
+        img, ill, x = base, None, base
+        mag, pw = ops.rps_spectrum(dev(img))
+    else:
+        img = np.clip(np.rint(base), 0, 65535).astype(np.uint16)
+        ill = (1.0 + 0.4 * rng.random(hw)) if kind.endswith("illum") else None
+        x = img.astype(np.float64) / ill if ill is not None else img.astype(np.float64)
+        mag, pw, corr = ops.rps_spectrum(dev(img), dev(ill) if ill is not None else None, want_corrected=True)
+        np.testing.assert_array_equal(host(corr), x)                      # the float64 divide of :145-150, exact
+    labels, e_mag, e_pow = o_qc.radial_power_spectrum(x)
+    np.testing.assert_allclose(host(mag), e_mag, rtol=1e-9)
+    np.testing.assert_allclose(host(pw), e_pow, rtol=1e-9)
+    slope = float(ops.loglog_slope(pw).item())
+    assert slope == pytest.approx(o_qc.power_loglog_slope(x), rel=1e-9, abs=1e-12)
+
+
+def test_rps_on_device_degenerate_cases():
+    require_gpu()
+    import torch
+    from image_processing_suite_b200 import ops
+    # constant image: no normalisation, zero spectrum, slope 0.0 (SURVEY.md section 4)
+    mag, pw = ops.rps_spectrum(dev(np.full((48, 64), 7.0)))
+    assert float(pw.abs().max()) == 0.0 and float(ops.loglog_slope(pw).item()) == 0.0
+    # 24 <= min(H, W) < 40: at most two rings -> 0.0
+    rng = np.random.default_rng(1)
+    mag, pw = ops.rps_spectrum(dev(rng.random((33, 50))))
+    assert pw.numel() == 2 and float(ops.loglog_slope(pw).item()) == 0.0
+    # min(H, W) < 24: no ring
+    mag, pw = ops.rps_spectrum(dev(rng.random((20, 30))))
+    assert pw.numel() == 0
+    # median of an even count with the two middle values apart, and with heavy ties
+    x = np.zeros((40, 40))
+    x[:20] = 10.0
+    x[0, 0] = 500.0
+    labels, e_mag, e_pow = o_qc.radial_power_spectrum(x)
+    mag, pw = ops.rps_spectrum(dev(x))
+    np.testing.assert_allclose(host(pw), e_pow, rtol=1e-9, atol=1e-9)
