@@ -58,6 +58,11 @@ PROTOTYPES = {
     "ips_loglog_slope": (i, [p, p, i, i, p]),
     "ips_cosine_workspace_bytes": (sz, [i, i]),
     "ips_cosine_triu": (i, [p, p, i, p, p, i, i, p, sz, p]),
+    "ips_cosine_planes_bytes": (sz, [i, i]),
+    "ips_cosine_plane_row_bytes": (sz, [i]),
+    "ips_cosine_plane_stride_bytes": (sz, [i, i]),
+    "ips_cosine_split_rows": (i, [p, i, i, i, i, p, p]),
+    "ips_cosine_triu_part": (i, [p, p, i, i, i, i, p]),
     "ips_cosine_pairs_workspace_bytes": (sz, [i, i]),
     "ips_cosine_triu_pairs": (i, [p, p, i, p, p, p, p, u64, i, i, p, sz, p]),
     "ips_well_mean_workspace_bytes": (sz, [i, i]),

@@ -143,6 +143,7 @@ __device__ __forceinline__ bool tc_tile_of(long long t, int nt, int nsb, int sb,
 __global__ void __launch_bounds__(256)
 cosine_split_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Xl,
                     int N, int D, int Dp) {
+  // X: the N rows to split; Xh / Xl already point at the first of their rows inside the planes
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
@@ -168,7 +169,8 @@ cosine_split_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ Xh,
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 cosine_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                 double* __restrict__ sum_out, int N, int nk, int nt, int nsb, int sb, long long n_tiles) {
+                 double* __restrict__ sum_out, int N, int nk, int nt, int nsb, int sb, long long t_begin,
+                 long long n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
@@ -199,7 +201,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (long long t = t_begin + blockIdx.x; t < n_tiles; t += gridDim.x) {
         int bi, bj;
         if (!tc_tile_of(t, nt, nsb, sb, bi, bj)) continue;
         for (int kb = 0; kb < nk; ++kb) {
@@ -219,7 +221,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (long long t = t_begin + blockIdx.x; t < n_tiles; t += gridDim.x) {
         int bi, bj;
         if (!tc_tile_of(t, nt, nsb, sb, bi, bj)) continue;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -251,7 +253,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     double warp_total = 0.0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (long long t = t_begin + blockIdx.x; t < n_tiles; t += gridDim.x) {
       int bi, bj;
       if (!tc_tile_of(t, nt, nsb, sb, bi, bj)) continue;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -322,16 +324,15 @@ size_t cosine_tc_workspace_bytes(int N, int D) {
   return 2 * round_up((size_t)N * Dp * sizeof(__nv_bfloat16), 1024);
 }
 
-// sum_out[0] must already be zero.  Returns IPS_OK or an error; the caller decides when to use it.
-int cosine_tc_launch(const float* X, double* sum_out, int N, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+// The tensor-core pass over slots [part * n / n_parts, (part + 1) * n / n_parts) of the tile schedule
+// (every slot is one 128 x 128 tile of the same cost, so equal slot counts are equal triangle areas).
+// planes: Xh [N][Dp] then Xl [N][Dp] (each rounded up to 1024 bytes).  sum_out[0] must already be zero.
+int cosine_tc_run(void* planes, double* sum_out, int N, int D, int part, int n_parts, cudaStream_t st) {
   const int Dp = (D + TC_BK - 1) / TC_BK * TC_BK;
   const size_t plane = round_up((size_t)N * Dp * sizeof(__nv_bfloat16), 1024);
-  if (ws == nullptr || ws_bytes < 2 * plane) IPS_FAIL(IPS_ERR_NOMEM, "cosine (tensor-core path): needs %zu workspace bytes", 2 * plane);
-  if (reinterpret_cast<uintptr_t>(ws) & 1023u) IPS_FAIL(IPS_ERR_BAD_ALIGN, "cosine (tensor-core path): workspace not 1024-byte aligned");
-  __nv_bfloat16* Xh = reinterpret_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16* Xl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + plane);
-  cosine_split_kernel<<<(N + 7) / 8, 256, 0, st>>>(X, Xh, Xl, N, D, Dp);
-  IPS_LAUNCH_OK("cosine_split_kernel");
+  if (reinterpret_cast<uintptr_t>(planes) & 1023u) IPS_FAIL(IPS_ERR_BAD_ALIGN, "cosine (tensor-core path): planes not 1024-byte aligned");
+  __nv_bfloat16* Xh = reinterpret_cast<__nv_bfloat16*>(planes);
+  __nv_bfloat16* Xl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(planes) + plane);
   CUtensorMap mh, ml;
   if (!make_map(&mh, Xh, N, Dp) || !make_map(&ml, Xl, N, Dp))
     IPS_FAIL(IPS_ERR_CUDA, "cosine (tensor-core path): cuTensorMapEncodeTiled failed");
@@ -344,11 +345,61 @@ int cosine_tc_launch(const float* X, double* sum_out, int N, int D, void* ws, si
   }();
   const int nsb = (nt + sb - 1) / sb;
   const long long n_slots = (long long)nsb * (nsb + 1) / 2 * (sb * sb);   // schedule slots, some empty
-  const long long n_real = (long long)nt * (nt + 1) / 2;
-  const int grid = (int)(n_real < (long long)sm_count() ? n_real : (long long)sm_count());
-  cosine_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mh, ml, sum_out, N, Dp / TC_BK, nt, nsb, sb, n_slots);
+  const long long t0 = n_slots * part / n_parts, t1 = n_slots * (part + 1) / n_parts;
+  if (t1 <= t0) return IPS_OK;
+  const long long span = t1 - t0;
+  const int grid = (int)(span < (long long)sm_count() ? span : (long long)sm_count());
+  cosine_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mh, ml, sum_out, N, Dp / TC_BK, nt, nsb, sb, t0, t1);
   IPS_LAUNCH_OK("cosine_tc_kernel");
   return IPS_OK;
 }
 
+int cosine_tc_split(const float* X_rows, int n_rows, int row0, int N, int D, void* planes, cudaStream_t st) {
+  const int Dp = (D + TC_BK - 1) / TC_BK * TC_BK;
+  const size_t plane = round_up((size_t)N * Dp * sizeof(__nv_bfloat16), 1024);
+  __nv_bfloat16* Xh = reinterpret_cast<__nv_bfloat16*>(planes) + (size_t)row0 * Dp;
+  __nv_bfloat16* Xl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(planes) + plane) + (size_t)row0 * Dp;
+  if (n_rows > 0) {
+    cosine_split_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(X_rows, Xh, Xl, n_rows, D, Dp);
+    IPS_LAUNCH_OK("cosine_split_kernel");
+  }
+  return IPS_OK;
+}
+
+// sum_out[0] must already be zero.  Returns IPS_OK or an error; the caller decides when to use it.
+int cosine_tc_launch(const float* X, double* sum_out, int N, int D, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int Dp = (D + TC_BK - 1) / TC_BK * TC_BK;
+  const size_t plane = round_up((size_t)N * Dp * sizeof(__nv_bfloat16), 1024);
+  if (ws == nullptr || ws_bytes < 2 * plane) IPS_FAIL(IPS_ERR_NOMEM, "cosine (tensor-core path): needs %zu workspace bytes", 2 * plane);
+  const int rc = cosine_tc_split(X, N, 0, N, D, ws, st);
+  if (rc != IPS_OK) return rc;
+  return cosine_tc_run(ws, sum_out, N, D, 0, 1, st);
+}
+
 }  // namespace ips
+
+using namespace ips;
+
+// ---- the contraction sharded over ranks ------------------------------
+extern "C" size_t ips_cosine_planes_bytes(int N, int D) { return N > 0 && D > 0 ? cosine_tc_workspace_bytes(N, D) : 0; }
+extern "C" size_t ips_cosine_plane_row_bytes(int D) { return (size_t)((D + TC_BK - 1) / TC_BK * TC_BK) * sizeof(__nv_bfloat16); }
+extern "C" size_t ips_cosine_plane_stride_bytes(int N, int D) { return N > 0 && D > 0 ? cosine_tc_workspace_bytes(N, D) / 2 : 0; }
+
+extern "C" int ips_cosine_split_rows(const float* X_rows, int n_rows, int row0, int N, int D, void* planes,
+                                     ips_stream_t stream) {
+  if (planes == nullptr || (n_rows > 0 && X_rows == nullptr)) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_cosine_split_rows: NULL pointer argument");
+  if (N <= 0 || D <= 0 || n_rows < 0 || row0 < 0 || row0 + n_rows > N)
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_cosine_split_rows: rows [%d, %d) outside 0..%d", row0, row0 + n_rows, N);
+  if (reinterpret_cast<uintptr_t>(planes) & 1023u) IPS_FAIL(IPS_ERR_BAD_ALIGN, "ips_cosine_split_rows: planes not 1024-byte aligned");
+  return cosine_tc_split(X_rows, n_rows, row0, N, D, planes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ips_cosine_triu_part(void* planes, double* sum_out, int N, int D, int part, int n_parts,
+                                    ips_stream_t stream) {
+  if (planes == nullptr || sum_out == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_cosine_triu_part: NULL pointer argument");
+  if (N < 2 || D <= 0 || n_parts < 1 || part < 0 || part >= n_parts)
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_cosine_triu_part: N=%d D=%d part %d of %d", N, D, part, n_parts);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  IPS_CUDA_OK(cudaMemsetAsync(sum_out, 0, sizeof(double), st));
+  return cosine_tc_run(planes, sum_out, N, D, part, n_parts, st);
+}

@@ -198,6 +198,23 @@ int ips_cosine_triu(const float* X, const int32_t* group, int n_groups, double* 
                     uint64_t* npairs_out, int N, int D, void* ws, size_t ws_bytes,
                     ips_stream_t stream);
 
+/* One large group sharded over ranks (BASELINE configs[4]: 10^6 x 3000).  The
+ * normalised rows live as two bf16 planes (hi, lo) of ips_cosine_planes_bytes(N, D) bytes, 1024-byte
+ * aligned: plane p starts at p * ips_cosine_plane_stride_bytes(N, D), a row is
+ * ips_cosine_plane_row_bytes(D) bytes.  Every rank normalises and splits its own rows into its slice
+ * (ips_cosine_split_rows), the slices are all-gathered once per plane (ips_allgather_blocks: rows as
+ * blocks), and every rank runs the tensor-core pass over its share of the upper-triangular tile
+ * schedule -- part `part` of `n_parts`, equal tile counts = equal triangle areas
+ * (ips_cosine_triu_part; sum_out[0] = that share's sum over i < j of cos(i, j)).  The partial sums are
+ * added in rank order by the caller.  N a multiple of n_parts is not required; pad with zero rows. */
+size_t ips_cosine_planes_bytes(int N, int D);
+size_t ips_cosine_plane_row_bytes(int D);
+size_t ips_cosine_plane_stride_bytes(int N, int D);
+int ips_cosine_split_rows(const float* X_rows, int n_rows, int row0, int N, int D, void* planes,
+                          ips_stream_t stream);
+int ips_cosine_triu_part(void* planes, double* sum_out, int N, int D, int part, int n_parts,
+                         ips_stream_t stream);
+
 /* As ips_cosine_triu (exact fp32 path) plus every pair's similarity: pairs_out holds, group
  * after group, the row-major strict upper triangle of the group's similarity matrix -- the
  * vector Pycyto_pertime.py:150-155 keeps as `cosine_similarities`; pair_offsets_out

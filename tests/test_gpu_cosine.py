@@ -93,3 +93,32 @@ def test_cosine_pairs_vector_matches_triu_values():
         np.testing.assert_allclose(got, ref, atol=ATOL)
         if ref.size:
             assert abs(float(host(s)[g]) - ref.sum()) < ATOL * ref.size
+
+
+def test_cosine_parts_of_the_tile_schedule_add_up():
+    """The sharded form on one GPU: the tensor-core pass over every third of the upper-triangular
+    tile schedule sums to the whole (ips_cosine_triu_part), and matches the closed form."""
+    torch = require_gpu()
+    import ctypes as C
+    from image_processing_suite_b200 import capi
+    from image_processing_suite_b200.cosine_parallel import ShardedCosine
+    n, d = 1500, 203
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((n, d), device="cuda", generator=g)
+    x[17] = 0                                                   # a zero row stays zero
+    sc = ShardedCosine(n, d)
+    whole = sc.sum_triu(x)
+    parts = []
+    part_sum = torch.zeros((1,), dtype=torch.float64, device="cuda")
+    for p in range(3):
+        capi.call("ips_cosine_triu_part", C.c_void_p(sc.planes.data_ptr()), C.c_void_p(part_sum.data_ptr()), n, d, p, 3, None)
+        parts.append(float(part_sum.item()))
+    xh = x.double()
+    nrm = xh.norm(dim=1, keepdim=True)
+    xh = torch.where(nrm > 0, xh / nrm, torch.zeros_like(xh))
+    ref = 0.5 * (float((xh.sum(0) ** 2).sum()) - float((xh * xh).sum()))
+    npairs = n * (n - 1) / 2
+    assert abs(sum(parts) - whole) / npairs < 1e-9
+    assert abs(whole - ref) / npairs < 1e-5                     # atol 1e-5 on the mean cosine
+    assert all(abs(p) > 0 for p in parts)
+    sc.close()
