@@ -37,6 +37,17 @@ def shard_wells(n_wells, rank, world):
     return list(range(rank, n_wells, world))
 
 
+def shard_units(n_plates, channels, rank=0, world=1):
+    """Illumination estimation reduces ACROSS the fields of a plate, so its unit of sharding is the
+    (plate, channel) pair, not the field: the units, plate-major, are dealt
+    round-robin over the ranks -- no collective, balanced to within one unit.  Returns this rank's
+    [(plate_index, channel), ...]."""
+    if not (0 <= rank < world):
+        raise ValueError("rank %d outside world %d" % (rank, world))
+    units = [(p, c) for p in range(int(n_plates)) for c in channels]
+    return units[rank::world]
+
+
 def plate_fields(n_wells, sites_per_well, rank=0, world=1):
     """(well, site) pairs of the rank's shard, wells ascending, sites 1..n inside a well."""
     return [(w, s) for w in shard_wells(n_wells, rank, world) for s in range(1, sites_per_well + 1)]

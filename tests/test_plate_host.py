@@ -108,3 +108,20 @@ def test_block_gather_protocol_gloo_world2(tmp_path):
     a = torch.load(tmp_path / "b0.pt")
     b = torch.load(tmp_path / "b1.pt")
     assert torch.equal(a, b)
+
+
+def test_illumination_units_are_dealt_once_and_evenly():
+    """K2 shards by (plate, channel), not by field: config 4 = 16 plate-timepoints
+    x 5 channels = 80 units over 8 ranks, no collective."""
+    chans = ["DNA", "ER", "RNA", "AGP", "Mito"]
+    seen = []
+    for r in range(8):
+        mine = plate.shard_units(16, chans, r, 8)
+        assert len(mine) == 10
+        seen += mine
+    assert sorted(seen) == sorted((p, c) for p in range(16) for c in chans)
+    sizes = [len(plate.shard_units(3, chans, r, 4)) for r in range(4)]
+    assert sum(sizes) == 15 and max(sizes) - min(sizes) <= 1
+    assert plate.shard_units(1, chans, 0, 1) == [(0, c) for c in chans]
+    with pytest.raises(ValueError):
+        plate.shard_units(2, chans, 4, 4)
