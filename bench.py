@@ -356,8 +356,31 @@ def gpu_arm(args):
     # fixed-size ncclAllGather per chunk and the launching thread never waits for the device
     # (ips_pack_rows_block -> ips_allgather_blocks -> ips_well_sums_add_blocks).
     block_rows = chunk_fields * n_max + 1
-    table = torch.zeros((n_chunks, world, block_rows, D_row), dtype=torch.float32, device=dev)
     gatherer = plate_mod.BlockGatherer()
+    # The bulk of the gather goes over NVSwitch peer memory with the copy engines (plate.PeerPusher:
+    # every block is stored into every peer's table as soon as it is final, no SM involved); the one
+    # NCCL all-gather that remains (the per-rank row totals, at the end of the plate) is the barrier.
+    # Without CUDA IPC the blocks themselves go through ncclAllGather, chunk by chunk.
+    pusher, push_note = None, "n/a (one rank)"
+    if world > 1 and not args.no_peer_push:
+        try:
+            table = plate_mod.exportable_zeros((n_chunks, world, block_rows, D_row))
+            pusher = plate_mod.PeerPusher(table)
+            push_note = "copy-engine stores into the peers' tables (CUDA IPC over NVLink), one NCCL all-gather of the row totals as barrier"
+        except Exception as e:                                  # IPC not available in this container
+            pusher, push_note = None, "unavailable (%s): ncclAllGather per chunk" % (str(e)[:80])
+    ok_all = torch.tensor([1 if (pusher is not None or world == 1) else 0], device=dev)
+    if dist is not None:
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)           # all ranks take the same path
+    if world > 1 and int(ok_all.item()) == 0:
+        if pusher is not None:
+            pusher.close()
+        pusher = None
+        if args.no_peer_push:
+            push_note = "disabled (--no-peer-push): ncclAllGather per chunk"
+    if pusher is None:
+        table = torch.zeros((n_chunks, world, block_rows, D_row), dtype=torch.float32, device=dev)
+    totals = torch.zeros((world, 1, D_row), dtype=torch.float32, device=dev)
     well_agg = plate_mod.WellAggregator(n_wells, D_row, device=dev)
     pack_ws = torch.empty(max(int(capi.call("ips_pack_rows_workspace_bytes", chunk_fields)), 16), dtype=torch.uint8, device=dev)
     agg_stream = torch.cuda.Stream(device=dev, priority=-1)   # its few CTAs must not queue behind a full fused grid
@@ -372,12 +395,21 @@ def gpu_arm(args):
             fs = slice(g * chunk_fields, (g + 1) * chunk_fields)
             plate_mod.pack_rows_block(plate_ints[fs], plate_flts[fs], plate_n[fs], field_well[fs], table[g, rank],
                                       field_base=g * chunk_fields, ws=pack_ws)
-            gatherer.gather(table[g])
+            if pusher is not None:
+                pusher.push(table[g, rank])
+            else:
+                gatherer.gather(table[g])
 
     def finish_plate():
         # Per-well sums run after the last field: measured at N = 8, folding them into the side
         # stream chunk by chunk slowed the field kernels by more (0.755 -> 0.794 ms per launch)
         # than the shorter tail gained (profiles/README.md).
+        if pusher is not None:
+            with torch.cuda.stream(agg_stream):               # the one NCCL all-gather: row totals + barrier
+                n_here = plate_n.clamp(min=0).sum()
+                totals[rank, 0, 0] = (n_here // 65536).to(torch.float32)
+                totals[rank, 0, 1] = (n_here % 65536).to(torch.float32)
+                gatherer.gather(totals)
         torch.cuda.current_stream().wait_stream(agg_stream)
         well_agg.reset()
         well_agg.add_blocks(table.view(n_chunks * world, block_rows, D_row))
@@ -660,10 +692,10 @@ def gpu_arm(args):
                          "algorithmic_bytes_per_launch": per_field[dom] * Fb + ill_b},
             "kernels": kernels,
             "aggregation": {"what": "pack rows -> %s -> per-well mean, inside the timed region" % (
-                                "NCCL all-gather of the plate's object rows (ips_allgather_rows) in %d chunks on a "
-                                "side stream (one fixed-size ncclAllGather per chunk, counts in block headers, no host "
-                                "sync), overlapping the remaining fields" % n_chunks if world > 1 else "no gather at N=1"),
-                            "check": agg_check,
+                                ("all-gather of the plate's object rows in %d chunks on a side stream, overlapping the "
+                                 "remaining fields (counts in block headers, no host sync)" % n_chunks) if world > 1
+                                else "no gather at N=1"),
+                            "check": agg_check, "bulk_transport": push_note,
                             "ms_after_last_step": ms_aggregate, "rows_per_rank": n_rows, "row_bytes": D_row * 4,
                             "gather_bytes_per_rank": n_rows * D_row * 4 if world > 1 else 0,
                             "wells": n_wells, "wells_with_rows": int((well_count_dev > 0).sum().item())},
@@ -696,6 +728,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=120.0)
     ap.add_argument("--ref-fields", type=int, default=8, help="distinct synthetic fields the reference arm cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-push", action="store_true", help="gather the row blocks with ncclAllGather instead of peer stores")
     ap.add_argument("--sustained-steps", type=int, default=216,
                     help="extra launches after the timed region for the sustained kernel figure (0 = skip)")
     args = ap.parse_args()

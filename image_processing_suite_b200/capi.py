@@ -96,6 +96,13 @@ PROTOTYPES = {
     "ips_allgather_rows": (i, [p, p, i64, i, p, p, i64, p]),
     "ips_allgather_blocks": (i, [p, p, i64, i, p]),
     "ips_comm_rank": (i, [p, C.POINTER(i), C.POINTER(i)]),
+    "ips_device_alloc": (i, [C.POINTER(p), sz]),
+    "ips_device_free": (i, [p]),
+    "ips_ipc_handle_bytes": (i, []),
+    "ips_ipc_export": (i, [p, p, i]),
+    "ips_peer_table_open": (i, [C.POINTER(p), p, i, i, p]),
+    "ips_peer_table_close": (i, [p]),
+    "ips_peer_push": (i, [p, sz, sz, p]),
     "ips_host_alloc": (i, [C.POINTER(p), sz]),
     "ips_host_alloc_flags": (i, [C.POINTER(p), sz, C.c_uint]),
     "ips_host_free": (i, [p]),

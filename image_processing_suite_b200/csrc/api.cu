@@ -71,3 +71,20 @@ extern "C" int ips_host_free(void* p) {
   if (p != nullptr) IPS_CUDA_OK(cudaFreeHost(p));
   return IPS_OK;
 }
+
+// Plain cudaMalloc / cudaFree: allocations of their own (not carved out of a caching allocator's
+// segment), as CUDA IPC export needs them (ips_ipc_export, plate.PeerPusher).
+extern "C" int ips_device_alloc(void** out, size_t bytes) {
+  if (out == nullptr) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_device_alloc: out is NULL");
+  cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    IPS_FAIL(e == cudaErrorMemoryAllocation ? IPS_ERR_NOMEM : IPS_ERR_CUDA, "ips_device_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  return IPS_OK;
+}
+
+extern "C" int ips_device_free(void* p) {
+  if (p != nullptr) IPS_CUDA_OK(cudaFree(p));
+  return IPS_OK;
+}

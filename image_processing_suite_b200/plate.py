@@ -160,6 +160,81 @@ class BlockGatherer:
             self._comm = None
 
 
+class _DeviceBlock:
+    """One cudaMalloc of its own, viewed as a torch tensor through __cuda_array_interface__."""
+
+    def __init__(self, shape, dtype=torch.float32):
+        self.shape = tuple(int(x) for x in shape)
+        n = 1
+        for x in self.shape:
+            n *= x
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        self.ptr = C.c_void_p()
+        capi.call("ips_device_alloc", C.byref(self.ptr), n * itemsize)
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.ptr.value, False),
+                                         "version": 2, "strides": None}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                capi.fn("ips_device_free")(self.ptr)
+        except Exception:
+            pass
+
+
+def exportable_zeros(shape, dtype=torch.float32):
+    """A zeroed device tensor on an allocation of its own (what ``PeerPusher`` can export)."""
+    blk = _DeviceBlock(shape, dtype)
+    t = torch.as_tensor(blk, device=torch.device("cuda", torch.cuda.current_device()))
+    t._ips_block = blk                            # keeps the allocation alive as long as the tensor
+    t.zero_()
+    return t
+
+
+class PeerPusher:
+    """The bulk of the row gather over NVSwitch peer memory (``ips_peer_push``): ``table`` is one
+    device allocation of the same shape on every rank; ``push(view)`` stores a contiguous view of it
+    into the same place of every peer's table with copy-engine transfers on the current stream --
+    no kernel, no SM.  ``BlockGatherer.gather`` on a small per-rank table at the end of the plate is
+    the barrier.  Raises IpsError when CUDA IPC is not available (the caller then gathers the blocks
+    with ``BlockGatherer`` alone)."""
+
+    def __init__(self, table, group=None):
+        import torch.distributed as dist
+        self.table = table
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        n = int(capi.call("ips_ipc_handle_bytes"))
+        buf = (C.c_char * n)()
+        if not hasattr(table, "_ips_block"):
+            raise ValueError("the table must come from plate.exportable_zeros (an allocation of its own)")
+        base = table.data_ptr()
+        capi.call("ips_ipc_export", C.c_void_p(base), C.cast(buf, C.c_void_p), n)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(buf), group=group)
+        blob = (C.c_char * (n * self.world)).from_buffer_copy(b"".join(handles))
+        h = C.c_void_p()
+        capi.call("ips_peer_table_open", C.byref(h), C.cast(blob, C.c_void_p), self.rank, self.world, C.c_void_p(base))
+        self._h = h
+
+    def push(self, view):
+        if not view.is_contiguous():
+            raise ValueError("push takes a contiguous view of the table")
+        off = view.data_ptr() - self.table.data_ptr()
+        nbytes = view.numel() * view.element_size()
+        if off < 0 or off + nbytes > self.table.numel() * self.table.element_size():
+            raise ValueError("the view is not inside the table")
+        dev = self.table.device
+        with torch.cuda.device(dev):
+            capi.call("ips_peer_push", self._h, off, nbytes, _stream(dev))
+
+    def close(self):
+        if self._h:
+            capi.call("ips_peer_table_close", self._h)
+            self._h = None
+
+
 def _make_comm(dist, group, rank, world):
     n = int(capi.call("ips_comm_unique_id_bytes"))
     buf = (C.c_char * n)()

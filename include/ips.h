@@ -375,6 +375,19 @@ int ips_allgather_rows(void* comm, const void* local_rows, int64_t n_local, int 
 int ips_allgather_blocks(void* comm, void* table, int64_t block_rows, int row_bytes,
                          ips_stream_t stream);
 int ips_comm_rank(void* comm, int* rank, int* world);
+/* The bulk of the same gather over NVSwitch peer memory, without SMs: every rank's table (same size,
+ * same layout, one cudaMalloc each) is exported with CUDA IPC (ips_ipc_export; the handles travel over
+ * the caller's control plane), ips_peer_table_open maps the peers' tables, and ips_peer_push stores
+ * a byte range of the local table into the same range of every peer's table with world - 1
+ * copy-engine transfers on `stream`.  Blocks are pushed as they become final; ONE ips_allgather_blocks
+ * at the end of the plate (on the per-rank totals) is the barrier that makes every push visible. */
+int ips_device_alloc(void** out, size_t bytes);   /* cudaMalloc of its own, exportable */
+int ips_device_free(void* p);
+int ips_ipc_handle_bytes(void);
+int ips_ipc_export(void* dev_ptr, void* handle_out, int bytes);
+int ips_peer_table_open(void** table_out, const void* handles, int rank, int world, void* own_table);
+int ips_peer_table_close(void* table);
+int ips_peer_push(void* table, size_t offset, size_t bytes, ips_stream_t stream);
 
 /* ---- host-buffer pipeline (the end-to-end call a script makes) -------------------------
  * One call = H2D of a batch of raw fields + label masks, K1, K3, D2H of max projections,

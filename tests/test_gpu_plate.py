@@ -127,3 +127,53 @@ def test_nccl_block_gather_content_two_gpus(tmp_path):
     b = torch.load(tmp_path / "n1.pt")
     assert torch.equal(a["table"], b["table"])
     assert torch.equal(a["count"], b["count"]) and torch.equal(a["mean"].view(torch.int64), b["mean"].view(torch.int64))
+
+
+def _push_worker(rank, world, port, tmp):
+    import os
+    import torch
+    import torch.distributed as dist
+    from image_processing_suite_b200 import plate
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        chunks, rows, D = 3, 50, 9
+        table = plate.exportable_zeros((chunks, world, rows, D))
+        pusher = plate.PeerPusher(table)
+        gatherer = plate.BlockGatherer(backend="ips")
+        totals = torch.zeros((world, 1, D), dtype=torch.float32, device="cuda")
+        for g in range(chunks):
+            table[g, rank] = torch.arange(rows * D, device="cuda", dtype=torch.float32).reshape(rows, D) + 1000 * rank + 100000 * g
+            pusher.push(table[g, rank])                    # copy-engine stores into the peer's table
+        totals[rank, 0, 0] = float(rank + 1)
+        gatherer.gather(totals)                            # the one NCCL all-gather = the barrier
+        torch.cuda.synchronize()
+        for g in range(chunks):
+            for r in range(world):
+                want = torch.arange(rows * D, dtype=torch.float32).reshape(rows, D) + 1000 * r + 100000 * g
+                assert torch.equal(table[g, r].cpu(), want), (g, r)
+        assert totals[:, 0, 0].cpu().tolist() == [float(r + 1) for r in range(world)]
+        with pytest.raises(ValueError):
+            plate.PeerPusher(torch.zeros((4, 4), device="cuda"))
+        pusher.close()
+        gatherer.close()
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_push_gather_two_gpus(tmp_path):
+    """The bulk transport bench.py uses at N > 1: every rank stores its blocks into the peers' tables
+    over NVLink (CUDA IPC, copy engines), one NCCL all-gather of the totals is the barrier."""
+    torch = require_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_push_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
