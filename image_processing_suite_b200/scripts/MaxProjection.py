@@ -120,24 +120,111 @@ def max_project_chunk(groups, bucket_name, s3_client):
     return written
 
 
-def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_client=None):
-    """The CLI loop of MaxProjection.py:64-95: plates, chunks of C*Z rows (plane-major,
-    channel-minor: channel j, plane p is row j + p*C), incomplete tail chunks skipped."""
-    s3_client = s3_client or storage.client()
+def _chunks_of(df, num_channels, num_planes):
+    """(plate, groups) per complete chunk of C*Z rows, in the reference's order (MaxProjection.py:75-90):
+    plane-major, channel-minor -- channel j, plane p is row j + p*C; incomplete tail chunks skipped."""
     group_size = num_channels * num_planes
-    df = read_csv_from_s3(bucket_data_set, data_set, s3_client)
-    total = 0
     for plate in df['PlateID'].unique():
         sub = df[df['PlateID'] == plate]
+        paths = [posixpath.join(str(a), str(b)) for a, b in zip(sub['Image_PathName'], sub['Image_FileName'])]
         for i in range(0, len(sub), group_size):
-            chunk = sub.iloc[i: i + group_size]
-            if len(chunk) < group_size:
+            if len(sub) - i < group_size:
                 logger.warning(f"Skipping incomplete chunk in plate {plate} at index {i}")
                 continue
-            groups = [[posixpath.join(chunk.iloc[j + p * num_channels].Image_PathName,
-                                      chunk.iloc[j + p * num_channels].Image_FileName)
-                       for p in range(num_planes)] for j in range(num_channels)]
-            total += max_project_chunk(groups, bucket_images, s3_client)
+            yield plate, [[paths[i + j + p * num_channels] for p in range(num_planes)] for j in range(num_channels)]
+
+
+def _project_staged(batch, chunks, num_channels, num_planes, bucket_name, s3_client, writers, out_ring):
+    """One staged batch of fields: one host->device copy of the compressed bytes, strips decoded on the
+    device, ONE fused z-max launch for all fields and channels, one device->host copy of the projections,
+    uploads on the writer threads.  Raises when the batch is not uniform (the caller then goes field by
+    field, which reports per channel group like the reference)."""
+    import torch
+    from .. import ops
+    from . import batchio
+    if not batch.ok():
+        raise ValueError("a file of the batch could not be staged")
+    src = batchio.to_device(batch)
+    planes = tiffio.decode_staged(src, batch.infos, batch.bases)                  # [B*C*Z][H][W]
+    B = len(chunks)
+    H, W = planes.shape[1:]
+    raw = planes.view(B, num_channels, num_planes, H, W)
+    proj = ops.preprocess_fused(raw, None, bin=1, want_binned=False)["maxproj"]    # [B][C][H][W]
+    host = out_ring.take((B, num_channels, H, W))
+    host.copy_(proj, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    head, tail = tiffio.plain_u16_parts(H, W)
+    pixels = host.numpy()
+    jobs = []
+    for b, (_, groups) in enumerate(chunks):
+        for j in range(num_channels):
+            key = modify_imagepath(groups[j][0])
+            jobs.append(writers.submit(storage.upload_parts, s3_client, [head, memoryview(pixels[b, j]).cast("B"), tail],
+                                       bucket_name, key))
+    out_ring.busy(host, jobs)
+    return B * num_channels
+
+
+class _PinnedRing:
+    """A few page-locked output buffers; one is handed out again only after its writes finished."""
+
+    def __init__(self, n=3):
+        self._bufs, self._jobs, self._n, self._at = {}, {}, n, 0
+
+    def take(self, shape):
+        import torch
+        k = self._at % self._n
+        self._at += 1
+        for f in self._jobs.pop(k, []):
+            f.result()
+        t = self._bufs.get(k)
+        count = 1
+        for x in shape:
+            count *= x
+        if t is None or t.numel() < count:
+            t = self._bufs[k] = torch.empty((count,), dtype=torch.uint16, pin_memory=True)
+        self._last = k
+        return t[:count].view(shape)
+
+    def busy(self, _tensor, jobs):
+        self._jobs[self._last] = jobs
+
+
+def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_client=None, batch_fields=8,
+        threads=8):
+    """The CLI loop of MaxProjection.py:64-95 at plate scale: the chunks (one field each) are staged
+    ``batch_fields`` at a time by reader threads (scripts/batchio.py), projected with one launch per
+    batch, and written by writer threads while the next batch is being read."""
+    from . import batchio
+    s3_client = s3_client or storage.client()
+    df = read_csv_from_s3(bucket_data_set, data_set, s3_client)
+    chunks = list(_chunks_of(df, num_channels, num_planes))
+    plates = [c[0] for c in chunks]
+
+    def batches():
+        for i in range(0, len(chunks), batch_fields):
+            part = chunks[i:i + batch_fields]
+            yield part, [storage.source_of(s3_client, bucket_images, k) for _, groups in part for g in groups for k in g]
+
+    loader = batchio.BatchLoader(batches(), threads=threads, depth=3)
+    writers = batchio.Writers(threads=max(2, threads // 2))
+    ring = _PinnedRing()
+    total = 0
+    for batch in loader:
+        part = batch.tag
+        try:
+            total += _project_staged(batch, part, num_channels, num_planes, bucket_images, s3_client, writers, ring)
+        except Exception as why:                      # mixed shapes, foreign formats, a missing file: field by field
+            logger.info(f"batch of {len(part)} fields goes field by field ({why})")
+            for _, groups in part:
+                total += max_project_chunk(groups, bucket_images, s3_client)
+        finally:
+            loader.release(batch)
+    writers.close()
+    for e in writers.errors:
+        logger.error(f"Error writing a projection: {e}")
+    total -= len(writers.errors)
+    for plate in dict.fromkeys(plates):
         logger.info(f"Plate {plate} finished! Check images in bucket.")
     return total
 

@@ -73,6 +73,19 @@ class LocalClient:
     def put_object(self, Bucket, Key, Body, ContentType=None):
         self.upload_fileobj(io.BytesIO(Body), Bucket, Key)
 
+    # not part of boto3: what the plate-scale loops use when the store is a directory
+    def local_path(self, Bucket, Key):
+        """Path of an object (readers ``readinto`` page-locked staging memory straight from it)."""
+        return os.path.join(self.root, Bucket, Key)
+
+    def upload_parts(self, parts, Bucket, Key):
+        """Write an object given as a sequence of buffers (no concatenation)."""
+        path = os.path.join(self.root, Bucket, Key)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            for part in parts:
+                f.write(part)
+
     def Bucket(self, name):
         return LocalBucket(self.root, name)
 
@@ -96,6 +109,20 @@ def resource():
         return LocalClient(root)
     import boto3
     return boto3.resource("s3")
+
+
+def source_of(client, bucket, key):
+    """A BatchLoader source for an object: its path on directory-backed storage, else a fetcher."""
+    if hasattr(client, "local_path"):
+        return client.local_path(bucket, key)
+    return lambda: client.get_object(Bucket=bucket, Key=key)['Body'].read()
+
+
+def upload_parts(client, parts, bucket, key):
+    if hasattr(client, "upload_parts"):
+        client.upload_parts(parts, bucket, key)
+    else:
+        client.upload_fileobj(io.BytesIO(b"".join(bytes(p) for p in parts)), bucket, key)
 
 
 def sniff_delimiter(text):

@@ -29,18 +29,24 @@ def read(path):
         return decode(f.read())
 
 
-def _encode_plain_u16(arr):
-    """Uncompressed little-endian baseline TIFF of a 2-D uint16 array: header, the pixels as one
-    strip, one IFD (what imageio.imwrite(..., format='tiff') amounts to, MaxProjection.py:48)."""
+def plain_u16_parts(h, w):
+    """(head, tail) of the uncompressed little-endian baseline TIFF of an h x w uint16 image: the
+    file is head + pixels + tail (header, the pixels as one strip, one IFD -- what
+    imageio.imwrite(..., format='tiff') amounts to, MaxProjection.py:48)."""
     import struct
-    h, w = arr.shape
-    data = np.ascontiguousarray(arr, dtype="<u2")
-    nbytes = data.nbytes
+    nbytes = h * w * 2
     pad = nbytes & 1
     tags = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8),
             (277, 3, 1, 1), (278, 4, 1, h), (279, 4, 1, nbytes)]
     ifd = struct.pack("<H", len(tags)) + b"".join(struct.pack("<HHII", *t) for t in tags) + struct.pack("<I", 0)
-    return b"".join([b"II*\x00", struct.pack("<I", 8 + nbytes + pad), memoryview(data).cast("B"), b"\x00" * pad, ifd])
+    return b"II*\x00" + struct.pack("<I", 8 + nbytes + pad), b"\x00" * pad + ifd
+
+
+def _encode_plain_u16(arr):
+    h, w = arr.shape
+    data = np.ascontiguousarray(arr, dtype="<u2")
+    head, tail = plain_u16_parts(h, w)
+    return b"".join([head, memoryview(data).cast("B"), tail])
 
 
 def encode(arr, compression=None):
@@ -126,37 +132,24 @@ def parse(data):
     return info
 
 
-def decode_to_device(files, device=None):
-    """list of TIFF byte strings of equal shape -> uint16 CUDA tensor [P][H][W].
-    Raises Unsupported (before touching the GPU) when any file is outside the device codec's
-    layout, ValueError when shapes differ or a strip is corrupt."""
-    import warnings
+def decode_staged(src, infos, bases, out=None):
+    """The device half of the codec: ``src`` is a uint8 CUDA tensor that holds whole TIFF files,
+    file p at byte ``bases[p]`` (16-byte aligned) with the IFD facts ``infos[p]`` (``parse``).
+    Returns the uint16 CUDA tensor [P][H][W] (``out`` if given).  LZW strips are decoded by
+    ips_tiff_lzw_decode, uncompressed strips are device-to-device copies; compressed bytes are all
+    that ever crossed PCIe.  ValueError when shapes differ or a strip is corrupt."""
     import torch
     from .. import ops
-    infos = [parse(f) for f in files]
     if not infos:
         raise ValueError("no files")
     h, w = infos[0]["height"], infos[0]["width"]
     if any((i["height"], i["width"]) != (h, w) for i in infos):
         raise ValueError("Image shape mismatch")
-    dev = torch.device(device if device is not None else "cuda")
+    dev = src.device
     plane = h * w * 2
-    out = torch.empty((len(files), h, w), dtype=torch.uint16, device=dev)
+    if out is None:
+        out = torch.empty((len(infos), h, w), dtype=torch.uint16, device=dev)
     dst = out.view(torch.uint8).reshape(-1)
-
-    def upload(view, data):            # bytes -> device, straight from the bytes object (the driver stages it once)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", UserWarning)          # torch.frombuffer on read-only bytes
-            view.copy_(torch.frombuffer(data, dtype=torch.uint8))
-
-    # LZW files go to a device buffer of compressed bytes; uncompressed strips straight to their pixels
-    lzw = [p for p, i in enumerate(infos) if i["compression"] == 5]
-    base = {}
-    total = 0
-    for p in lzw:
-        base[p] = total
-        total += (len(files[p]) + 15) // 16 * 16
-    src = torch.empty((max(total, 16),), dtype=torch.uint8, device=dev)
     so, sb, do, db = [], [], [], []
     for p, i in enumerate(infos):
         rps = i["rows_per_strip"]
@@ -164,8 +157,7 @@ def decode_to_device(files, device=None):
         rows = np.minimum(rps, h - rps * np.arange(len(offs), dtype=np.int64))
         d0, dn = p * plane + rps * w * 2 * np.arange(len(offs), dtype=np.int64), rows * w * 2
         if i["compression"] == 5:
-            upload(src[base[p]:base[p] + len(files[p])], files[p])
-            so.append(base[p] + offs)
+            so.append(int(bases[p]) + offs)
             sb.append(cnts)
             do.append(d0)
             db.append(dn)
@@ -173,10 +165,11 @@ def decode_to_device(files, device=None):
         if np.any(cnts < dn):
             raise ValueError("an uncompressed strip of file %d is short" % p)
         if np.all(offs[1:] == offs[:-1] + dn[:-1]):                 # the usual case: one run of pixels
-            upload(dst[p * plane:(p + 1) * plane], memoryview(files[p])[int(offs[0]):int(offs[0]) + plane])
+            o = int(bases[p]) + int(offs[0])
+            dst[p * plane:(p + 1) * plane].copy_(src[o:o + plane], non_blocking=True)
         else:
             for o, a, n in zip(offs, d0, dn):
-                upload(dst[int(a):int(a + n)], memoryview(files[p])[int(o):int(o + n)])
+                dst[int(a):int(a + n)].copy_(src[int(bases[p]) + int(o):int(bases[p]) + int(o + n)], non_blocking=True)
     if so:
         so, sb, do, db = (np.concatenate(x) for x in (so, sb, do, db))
         status = ops.tiff_lzw_decode(src, so, sb, dst, do, db)
@@ -189,6 +182,30 @@ def decode_to_device(files, device=None):
         if i["big_endian"] or i["predictor"] == 2:
             ops.tiff_fix_u16(out[p], predictor=i["predictor"], byteswap=i["big_endian"])
     return out
+
+
+def decode_to_device(files, device=None):
+    """list of TIFF byte strings of equal shape -> uint16 CUDA tensor [P][H][W].
+    Raises Unsupported (before touching the GPU) when any file is outside the device codec's
+    layout, ValueError when shapes differ or a strip is corrupt."""
+    import warnings
+    import torch
+    infos = [parse(f) for f in files]
+    if not infos:
+        raise ValueError("no files")
+    if any((i["height"], i["width"]) != (infos[0]["height"], infos[0]["width"]) for i in infos):
+        raise ValueError("Image shape mismatch")
+    dev = torch.device(device if device is not None else "cuda")
+    bases, total = [], 0
+    for f in files:
+        bases.append(total)
+        total += (len(f) + 15) // 16 * 16
+    src = torch.empty((max(total, 16),), dtype=torch.uint8, device=dev)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)              # torch.frombuffer on read-only bytes
+        for f, b in zip(files, bases):    # bytes -> device, straight from the bytes object (the driver stages it once)
+            src[b:b + len(f)].copy_(torch.frombuffer(f, dtype=torch.uint8))
+    return decode_staged(src, infos, bases)
 
 
 def encode_lzw_from_device(planes, rows_per_strip=None):
