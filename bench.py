@@ -625,6 +625,18 @@ def gpu_arm(args):
     if rank == 0 and world == 1:
         secondary = secondary_kernels(k1_out[0]["maxproj"][0].contiguous())
 
+    # ---- the drop-in scripts on files (rank 0, N=1 only): TIFF files in -> TIFF / CSV files out -------
+    e2e_files = None
+    if rank == 0 and world == 1 and not args.no_files:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("bench_files", os.path.join(ROOT, "tools", "bench_files.py"))
+            bf = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bf)
+            e2e_files = bf.main(["--sites", str(args.files_sites), "--distinct", "4", "--cpu-sites", "1"])
+        except Exception as e:                                   # the headline numbers must not depend on this block
+            e2e_files = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -700,6 +712,7 @@ def gpu_arm(args):
                             "gather_bytes_per_rank": n_rows * D_row * 4 if world > 1 else 0,
                             "wells": n_wells, "wells_with_rows": int((well_count_dev > 0).sum().item())},
             "cpu_baseline": cpu,
+            "e2e_files": e2e_files,
             "secondary": secondary,
             "clocks": clocks.summary(),
             "objects_last_field": int(n_obj_last[-1]),
@@ -728,6 +741,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=120.0)
     ap.add_argument("--ref-fields", type=int, default=8, help="distinct synthetic fields the reference arm cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the file-level run of the drop-in scripts (e2e_files)")
+    ap.add_argument("--files-sites", type=int, default=96)
     ap.add_argument("--no-peer-push", action="store_true", help="gather the row blocks with ncclAllGather instead of peer stores")
     ap.add_argument("--sustained-steps", type=int, default=216,
                     help="extra launches after the timed region for the sustained kernel figure (0 = skip)")

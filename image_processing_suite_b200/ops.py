@@ -598,7 +598,7 @@ def tiff_lzw_encode(planes, rows_per_strip=None):
     return files, host
 
 
-def tiff_lzw_decode(src, src_off, src_bytes, dst, dst_off, dst_bytes):
+def tiff_lzw_decode(src, src_off, src_bytes, dst, dst_off, dst_bytes, to_host=True):
     """LZW strips src[src_off[s] : +src_bytes[s]] -> dst[dst_off[s] : +dst_bytes[s]] (uint8 views,
     device).  The descriptor arrays are host sequences or NumPy arrays.  Returns the per-strip status (host
     int32 tensor; 0 = ok).  Replaces the strip decoding behind Image.open / imageio.imread
@@ -625,7 +625,7 @@ def tiff_lzw_decode(src, src_off, src_bytes, dst, dst_off, dst_bytes):
         status = torch.empty((n,), dtype=torch.int32, device=dev)
         capi.call("ips_tiff_lzw_decode", _ptr(src), _ptr(desc64[0]), _ptr(desc32[0]), _ptr(dst), _ptr(desc64[1]),
                   _ptr(desc32[1]), n, _ptr(status), _stream(dev))
-        return status.cpu()
+        return status.cpu() if to_host else status          # to_host=False: the caller reads it after its own sync
 
 
 def tiff_fix_u16(img, predictor=1, byteswap=False):

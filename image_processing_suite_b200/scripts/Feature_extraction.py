@@ -123,10 +123,13 @@ class _ObjectCsv:
         prev = self._last
 
         def write():
-            if prev is not None:
-                prev.result()                      # batches land in the file in order
             import pyarrow.csv as pacsv
-            pacsv.write_csv(table, self._file, write_options=pacsv.WriteOptions(include_header=False, quoting_style="none"))
+            sink = pa.BufferOutputStream()         # formatted on this thread, in parallel with the other batches
+            pacsv.write_csv(table, sink, write_options=pacsv.WriteOptions(include_header=False, quoting_style="none"))
+            text = sink.getvalue()
+            if prev is not None:
+                prev.result()                      # ... and appended to the file in batch order
+            self._file.write(memoryview(text))
         self._last = self._writers.submit(write)
 
     def close(self):
@@ -171,7 +174,7 @@ def run(data_file, output, image_dir=None, batch=8, raw_intensities=False, threa
         for i in range(0, len(site_files), batch):
             yield (i, min(i + batch, len(site_files))), [p for site in site_files[i:i + batch] for p in site]
 
-    writers = batchio.Writers(threads=max(2, threads // 2))
+    writers = batchio.Writers(threads=max(2, threads))
     csvs = {o: _ObjectCsv(os.path.join(output, f'{o}.csv'), channels, writers) for o in objects}
     counts = {o: np.zeros(len(site_files), np.int64) for o in objects}
 
@@ -200,14 +203,26 @@ def run(data_file, output, image_dir=None, batch=8, raw_intensities=False, threa
             counts[o][i0:i0 + B] = host_n
 
     loader = batchio.BatchLoader(batches(), threads=threads, depth=3)
-    for staged in loader:
+    import time
+    trace = batchio.Trace()
+    it = iter(loader)
+    while True:
+        t0 = time.perf_counter()
+        staged = next(it, None)
+        trace.add("wait for staged files", t0)
+        if staged is None:
+            break
         i0, i1 = staged.tag
         try:
             if not staged.ok():
                 raise ValueError("a file of the batch is not a TIFF the device codec reads")
+            t0 = time.perf_counter()
             src = batchio.to_device(staged)
             planes = tiffio.decode_staged(src, staged.infos, staged.bases)
+            trace.add("copy + decode", t0)
+            t0 = time.perf_counter()
             measure(i0, planes.view(i1 - i0, C_ + O_, planes.shape[1], planes.shape[2]))
+            trace.add("measure + rows to host", t0)
         except (ValueError, tiffio.Unsupported) as why:
             # 8-bit / tiled / deflate images or masks, mixed shapes: the host decoder, site by site
             logger.info("sites %d-%d use the host image decoder (%s)", i0 + 1, i1, why)
@@ -221,9 +236,12 @@ def run(data_file, output, image_dir=None, batch=8, raw_intensities=False, threa
                 measure(i, torch.cat([img, torch.stack(labs)])[None])
         finally:
             loader.release(staged)
+    t0 = time.perf_counter()
     for o in objects:
         csvs[o].close()
     writers.close()
+    trace.add("wait for writers", t0)
+    trace.report(logger, "Feature_extraction")
     if writers.errors:
         raise IOError("writing the object tables failed: %s" % writers.errors[0])
     image_df = pd.DataFrame(rows_meta)

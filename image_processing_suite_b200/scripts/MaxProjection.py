@@ -134,34 +134,51 @@ def _chunks_of(df, num_channels, num_planes):
             yield plate, [[paths[i + j + p * num_channels] for p in range(num_planes)] for j in range(num_channels)]
 
 
-def _project_staged(batch, chunks, num_channels, num_planes, bucket_name, s3_client, writers, out_ring):
-    """One staged batch of fields: one host->device copy of the compressed bytes, strips decoded on the
-    device, ONE fused z-max launch for all fields and channels, one device->host copy of the projections,
-    uploads on the writer threads.  Raises when the batch is not uniform (the caller then goes field by
-    field, which reports per channel group like the reference)."""
+class _InFlight:
+    """One batch on the device: everything up to the device->host copy of the projections is queued on
+    ``stream``; ``finish`` waits for it, checks the decoder's status and hands the files to the writers."""
+
+    def __init__(self, batch, chunks, stream, host, check, shape, keep):
+        self.batch, self.chunks, self.stream, self.host, self.check, self.shape, self.keep = \
+            batch, chunks, stream, host, check, shape, keep
+
+
+def _enqueue_staged(batch, chunks, num_channels, num_planes, stream, out_ring):
+    """Queue one staged batch of fields on ``stream`` without waiting for the device: one host->device copy
+    of the (still compressed) bytes, strips decoded on the device, ONE fused z-max launch for all fields and
+    channels, one device->host copy of the projections.  Raises when the batch is not uniform (the caller
+    then goes field by field, which reports per channel group like the reference)."""
     import torch
     from .. import ops
     from . import batchio
     if not batch.ok():
         raise ValueError("a file of the batch could not be staged")
-    src = batchio.to_device(batch)
-    planes = tiffio.decode_staged(src, batch.infos, batch.bases)                  # [B*C*Z][H][W]
-    B = len(chunks)
-    H, W = planes.shape[1:]
-    raw = planes.view(B, num_channels, num_planes, H, W)
-    proj = ops.preprocess_fused(raw, None, bin=1, want_binned=False)["maxproj"]    # [B][C][H][W]
-    host = out_ring.take((B, num_channels, H, W))
-    host.copy_(proj, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    with torch.cuda.stream(stream):
+        src = batchio.to_device(batch)
+        planes, check = tiffio.decode_staged(src, batch.infos, batch.bases, defer_check=True)      # [B*C*Z][H][W]
+        B = len(chunks)
+        H, W = planes.shape[1:]
+        raw = planes.view(B, num_channels, num_planes, H, W)
+        proj = ops.preprocess_fused(raw, None, bin=1, want_binned=False)["maxproj"]                # [B][C][H][W]
+        host = out_ring.take((B, num_channels, H, W))
+        host.copy_(proj, non_blocking=True)
+    return _InFlight(batch, chunks, stream, host, check, (B, num_channels, H, W), (src, planes, proj))
+
+
+def _finish_staged(job, num_channels, bucket_name, s3_client, writers, out_ring):
+    job.stream.synchronize()
+    job.check()
+    B, _, H, W = job.shape
     head, tail = tiffio.plain_u16_parts(H, W)
-    pixels = host.numpy()
+    pixels = job.host.numpy()
     jobs = []
-    for b, (_, groups) in enumerate(chunks):
+    for b, (_, groups) in enumerate(job.chunks):
         for j in range(num_channels):
             key = modify_imagepath(groups[j][0])
             jobs.append(writers.submit(storage.upload_parts, s3_client, [head, memoryview(pixels[b, j]).cast("B"), tail],
                                        bucket_name, key))
-    out_ring.busy(host, jobs)
+    out_ring.busy(job.host, jobs)
+    job.keep = None
     return B * num_channels
 
 
@@ -169,7 +186,7 @@ class _PinnedRing:
     """A few page-locked output buffers; one is handed out again only after its writes finished."""
 
     def __init__(self, n=3):
-        self._bufs, self._jobs, self._n, self._at = {}, {}, n, 0
+        self._bufs, self._jobs, self._n, self._at, self._slot_of = {}, {}, n, 0, {}
 
     def take(self, shape):
         import torch
@@ -183,15 +200,16 @@ class _PinnedRing:
             count *= x
         if t is None or t.numel() < count:
             t = self._bufs[k] = torch.empty((count,), dtype=torch.uint16, pin_memory=True)
-        self._last = k
-        return t[:count].view(shape)
+        view = t[:count].view(shape)
+        self._slot_of[view.data_ptr()] = k
+        return view
 
-    def busy(self, _tensor, jobs):
-        self._jobs[self._last] = jobs
+    def busy(self, tensor, jobs):
+        self._jobs[self._slot_of[tensor.data_ptr()]] = jobs
 
 
-def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_client=None, batch_fields=8,
-        threads=8):
+def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_client=None, batch_fields=4,
+        threads=12):
     """The CLI loop of MaxProjection.py:64-95 at plate scale: the chunks (one field each) are staged
     ``batch_fields`` at a time by reader threads (scripts/batchio.py), projected with one launch per
     batch, and written by writer threads while the next batch is being read."""
@@ -206,21 +224,56 @@ def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_c
             part = chunks[i:i + batch_fields]
             yield part, [storage.source_of(s3_client, bucket_images, k) for _, groups in part for g in groups for k in g]
 
-    loader = batchio.BatchLoader(batches(), threads=threads, depth=3)
-    writers = batchio.Writers(threads=max(2, threads // 2))
-    ring = _PinnedRing()
+    import time
+    import torch
+    loader = batchio.BatchLoader(batches(), threads=threads, depth=4)
+    writers = batchio.Writers(threads=max(2, threads))          # 47 MB of projections per field leave through these
+    ring = _PinnedRing(4)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    trace = batchio.Trace()
     total = 0
-    for batch in loader:
-        part = batch.tag
+    flying = []                                   # batches queued on the device, oldest first (at most two)
+
+    def land(job):
+        nonlocal total
+        t0 = time.perf_counter()
         try:
-            total += _project_staged(batch, part, num_channels, num_planes, bucket_images, s3_client, writers, ring)
+            total += _finish_staged(job, num_channels, bucket_images, s3_client, writers, ring)
+        except Exception as why:                  # a damaged strip: that batch again, field by field
+            logger.info(f"batch of {len(job.chunks)} fields goes field by field ({why})")
+            for _, groups in job.chunks:
+                total += max_project_chunk(groups, bucket_images, s3_client)
+        finally:
+            loader.release(job.batch)
+        trace.add("wait for the device + hand to writers", t0)
+
+    it = iter(loader)
+    k = 0
+    while True:
+        t0 = time.perf_counter()
+        batch = next(it, None)
+        trace.add("wait for staged files", t0)
+        if batch is None:
+            break
+        part = batch.tag
+        t0 = time.perf_counter()
+        try:
+            flying.append(_enqueue_staged(batch, part, num_channels, num_planes, streams[k % 2], ring))
+            k += 1
         except Exception as why:                      # mixed shapes, foreign formats, a missing file: field by field
             logger.info(f"batch of {len(part)} fields goes field by field ({why})")
             for _, groups in part:
                 total += max_project_chunk(groups, bucket_images, s3_client)
-        finally:
             loader.release(batch)
+        trace.add("queue copy + decode + project + read back", t0)
+        while len(flying) > 1:                        # batch i runs on the device while batch i - 1 is written
+            land(flying.pop(0))
+    while flying:
+        land(flying.pop(0))
+    t0 = time.perf_counter()
     writers.close()
+    trace.add("wait for writers", t0)
+    trace.report(logger, "MaxProjection")
     for e in writers.errors:
         logger.error(f"Error writing a projection: {e}")
     total -= len(writers.errors)

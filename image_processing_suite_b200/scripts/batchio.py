@@ -26,6 +26,46 @@ def _align16(n):
     return (int(n) + 15) // 16 * 16
 
 
+# Page-locking memory is slow (hundreds of milliseconds per gigabyte): staging slots are kept for the
+# life of the process and handed from one loader to the next.
+_SLOT_POOL = []
+_SLOT_LOCK = threading.Lock()
+
+
+def _take_slot(nbytes):
+    from ..pipeline import pinned_empty
+    with _SLOT_LOCK:
+        fit = [k for k, s in enumerate(_SLOT_POOL) if s.shape[0] >= nbytes]
+        if fit:
+            return _SLOT_POOL.pop(min(fit, key=lambda k: _SLOT_POOL[k].shape[0]))
+    return pinned_empty((int(nbytes),), np.uint8)
+
+
+def _give_slot(slot):
+    with _SLOT_LOCK:
+        _SLOT_POOL.append(slot)
+        _SLOT_POOL.sort(key=lambda s: -s.shape[0])
+        del _SLOT_POOL[6:]
+
+
+class Trace:
+    """Wall-clock seconds per stage of a plate loop (IPS_IO_TRACE=1 prints them)."""
+
+    def __init__(self):
+        import os
+        self.on = os.environ.get("IPS_IO_TRACE", "") not in ("", "0")
+        self.t = {}
+
+    def add(self, key, t0):
+        import time
+        if self.on:
+            self.t[key] = self.t.get(key, 0.0) + time.perf_counter() - t0
+
+    def report(self, log, what):
+        if self.on:
+            log.info("%s stages (s): %s", what, ", ".join("%s %.3f" % kv for kv in sorted(self.t.items())))
+
+
 class StagedBatch:
     """The files of one batch in page-locked memory: ``buf`` (uint8), ``bases`` / ``sizes`` per file,
     ``infos`` (tiffio.parse) or the exception that file raised, ``tag`` (caller's bookkeeping)."""
@@ -49,14 +89,12 @@ class BatchLoader:
     ``release(batch)`` when the device copy of ``batch.buf`` has been issued AND has completed
     (the staging slot is reused)."""
 
-    def __init__(self, batches, threads=8, depth=3, slot_bytes=1 << 28):
-        from ..pipeline import pinned_empty
+    def __init__(self, batches, threads=8, depth=3, slot_bytes=1 << 26):
         self._batches = iter(batches)
         self._pool = cf.ThreadPoolExecutor(max_workers=max(1, threads), thread_name_prefix="ips-read")
         self._depth = max(1, depth)
         self._slot_bytes = int(slot_bytes)
-        self._pinned = pinned_empty
-        self._free = [self._pinned((self._slot_bytes,), np.uint8) for _ in range(self._depth)]
+        self._free = [None] * self._depth       # slots are taken from the process-wide pool when a batch's size is known
         self._lock = threading.Lock()
         self._pending = []          # futures of staged batches, in order
         self._done = False
@@ -109,8 +147,11 @@ class BatchLoader:
         for z in sizes:
             bases.append(at)
             at += _align16(z)
-        if at > slot.shape[0]:
-            slot = self._pinned((max(at, 2 * slot.shape[0]),), np.uint8)        # grow: this batch is larger than the slots
+        if slot is None or at > slot.shape[0]:
+            if slot is not None:
+                _give_slot(slot)
+            self._slot_bytes = max(self._slot_bytes, at + at // 8)            # room for the slightly larger batches to come
+            slot = _take_slot(self._slot_bytes)
         mv = memoryview(slot)
         futs = [self._pool.submit(self._read_one, s, mv[b:b + max(z, 1)]) for s, b, z in zip(sources, bases, sizes)]
         got = [f.result() for f in futs]
@@ -148,7 +189,7 @@ class BatchLoader:
     def __next__(self):
         self._fill()
         if not self._pending:
-            self._pool.shutdown(wait=False)
+            self.close()
             raise StopIteration
         batch = self._pending.pop(0).result()
         self._fill()
@@ -162,6 +203,11 @@ class BatchLoader:
 
     def close(self):
         self._pool.shutdown(wait=False)
+        with self._lock:
+            for slot in self._free:
+                if slot is not None:
+                    _give_slot(slot)
+            self._free = []
 
 
 def to_device(batch, device="cuda", stream=None):

@@ -132,12 +132,14 @@ def parse(data):
     return info
 
 
-def decode_staged(src, infos, bases, out=None):
+def decode_staged(src, infos, bases, out=None, defer_check=False):
     """The device half of the codec: ``src`` is a uint8 CUDA tensor that holds whole TIFF files,
     file p at byte ``bases[p]`` (16-byte aligned) with the IFD facts ``infos[p]`` (``parse``).
     Returns the uint16 CUDA tensor [P][H][W] (``out`` if given).  LZW strips are decoded by
     ips_tiff_lzw_decode, uncompressed strips are device-to-device copies; compressed bytes are all
-    that ever crossed PCIe.  ValueError when shapes differ or a strip is corrupt."""
+    that ever crossed PCIe.  ValueError when shapes differ or a strip is corrupt.
+    ``defer_check``: do not wait for the decoder here; returns (out, check) and the caller runs
+    ``check()`` once the stream has been synchronised (a pipelined loop must not block per batch)."""
     import torch
     from .. import ops
     if not infos:
@@ -170,18 +172,26 @@ def decode_staged(src, infos, bases, out=None):
         else:
             for o, a, n in zip(offs, d0, dn):
                 dst[int(a):int(a + n)].copy_(src[int(bases[p]) + int(o):int(bases[p]) + int(o + n)], non_blocking=True)
+    status = None
     if so:
         so, sb, do, db = (np.concatenate(x) for x in (so, sb, do, db))
-        status = ops.tiff_lzw_decode(src, so, sb, dst, do, db)
-        if int(status.max()) != 0:
-            bad = int(torch.nonzero(status)[0])
-            if int(status[bad]) == 3:
+        status = ops.tiff_lzw_decode(src, so, sb, dst, do, db, to_host=not defer_check)
+
+    def check():
+        if status is None:
+            return
+        st = status.cpu() if status.is_cuda else status
+        if int(st.max()) != 0:
+            bad = int(torch.nonzero(st)[0])
+            if int(st[bad]) == 3:
                 raise Unsupported("pre-6.0 (LSB-first) LZW strip")          # libtiff still reads those: host decode
-            raise ValueError("LZW strip %d is damaged (status %d)" % (bad, int(status[bad])))
+            raise ValueError("LZW strip %d is damaged (status %d)" % (bad, int(st[bad])))
+    if not defer_check:
+        check()
     for p, i in enumerate(infos):
         if i["big_endian"] or i["predictor"] == 2:
             ops.tiff_fix_u16(out[p], predictor=i["predictor"], byteswap=i["big_endian"])
-    return out
+    return (out, check) if defer_check else out
 
 
 def decode_to_device(files, device=None):

@@ -197,40 +197,41 @@ def test_normalize_script_matches_pandas_and_oracle(tmp_path, monkeypatch, qc_dr
     pm = pd.DataFrame({"Metadata_Well": wells, "Metadata_Plate": "P1", "Metadata_ConcLevel": 1,
                        "Metadata_Compound": ["dmso" if i % 4 == 0 else f"cmp{i}" for i in range(len(wells))]})
     s3.put_object(Bucket="b", Key="exp/Plate_P1_PlateMap.csv", Body=pm.to_csv(index=False).encode())
-    keys = nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", "mean", False, qc_drop, s3)
-    assert keys == ["norm/P1/Normalized_features_24h.csv"]
-    got = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key=keys[0])["Body"].read()))
-    # ---- the same steps in pandas + the oracle's mad_robustize -------------------------------
-    image_df = pd.DataFrame(rows_img)
-    failing = image_df.loc[image_df.filter(like="ImageQC_").any(axis=1), "ImageNumber"]
-    per_table = []
-    for name, prefix in nz.TABLE_PREFIX.items():
-        df = image_df if name == "Image" else pd.DataFrame(tabs[name]).merge(
-            image_df[["ImageNumber", "Metadata_Well", "Metadata_Site"]], on="ImageNumber", how="left")
-        if qc_drop:
-            df = df[~df["ImageNumber"].isin(failing)]
-        keep = {"Metadata_Well", "Metadata_Site"} if qc_drop else {"Metadata_Well"}
-        df = df.drop(columns=[c for c in df.columns if c == "ImageNumber" or (c.startswith("Metadata") and c not in keep)
-                              or any(s in c for s in nz.DROP_SUBSTRINGS)])
-        df = df.rename(columns=lambda x: prefix + x if not x.startswith("Metadata_") else x)
-        if qc_drop:
-            sc = df.groupby("Metadata_Well")["Metadata_Site"].nunique()
-            df = df.merge((sc.max() / sc).rename("scaling_factor"), on="Metadata_Well")
-            ints = [c for c in df.select_dtypes(include="integer").columns if not c.startswith("Metadata")]
-            df[ints] = df[ints].multiply(df["scaling_factor"], axis=0)
-            df = df.drop(columns=["scaling_factor", "Metadata_Site"])
-        per_table.append(df.groupby("Metadata_Well", as_index=False).agg("mean"))
-    merged = reduce(lambda l, r: pd.merge(l, r, on="Metadata_Well", how="outer"), per_table)
-    pm2 = pm[["Metadata_Compound", "Metadata_ConcLevel", "Metadata_Well", "Metadata_Plate"]].copy()
-    pm2["Metadata_Compound"] = pm2["Metadata_Compound"].str.upper()
-    merged = pm2.merge(merged, on="Metadata_Well", how="inner")
-    feats = [c for c in merged.columns if "Metadata" not in c]
-    z = o_norm.mad_robustize(merged[feats].to_numpy(float), (merged["Metadata_Compound"] == "DMSO").to_numpy())
-    assert list(got.columns) == [c for c in merged.columns if c not in feats] + ["Metadata_Timepoint"] + feats
-    assert list(got["Metadata_Well"]) == list(merged["Metadata_Well"])
-    np.testing.assert_allclose(got[feats].to_numpy(float), z, rtol=1e-9, atol=1e-9)
+    for agg in ("mean", "median"):                         # --well_agg_func (Normalize_CP_ami.py:126,163)
+        keys = nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", agg, False, qc_drop, s3)
+        assert keys == ["norm/P1/Normalized_features_24h.csv"]
+        got = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key=keys[0])["Body"].read()))
+        # ---- the same steps in pandas + the oracle's mad_robustize -------------------------------
+        image_df = pd.DataFrame(rows_img)
+        failing = image_df.loc[image_df.filter(like="ImageQC_").any(axis=1), "ImageNumber"]
+        per_table = []
+        for name, prefix in nz.TABLE_PREFIX.items():
+            df = image_df if name == "Image" else pd.DataFrame(tabs[name]).merge(
+                image_df[["ImageNumber", "Metadata_Well", "Metadata_Site"]], on="ImageNumber", how="left")
+            if qc_drop:
+                df = df[~df["ImageNumber"].isin(failing)]
+            keep = {"Metadata_Well", "Metadata_Site"} if qc_drop else {"Metadata_Well"}
+            df = df.drop(columns=[c for c in df.columns if c == "ImageNumber" or (c.startswith("Metadata") and c not in keep)
+                                  or any(s in c for s in nz.DROP_SUBSTRINGS)])
+            df = df.rename(columns=lambda x: prefix + x if not x.startswith("Metadata_") else x)
+            if qc_drop:
+                sc = df.groupby("Metadata_Well")["Metadata_Site"].nunique()
+                df = df.merge((sc.max() / sc).rename("scaling_factor"), on="Metadata_Well")
+                ints = [c for c in df.select_dtypes(include="integer").columns if not c.startswith("Metadata")]
+                df[ints] = df[ints].multiply(df["scaling_factor"], axis=0)
+                df = df.drop(columns=["scaling_factor", "Metadata_Site"])
+            per_table.append(df.groupby("Metadata_Well", as_index=False).agg(agg))
+        merged = reduce(lambda l, r: pd.merge(l, r, on="Metadata_Well", how="outer"), per_table)
+        pm2 = pm[["Metadata_Compound", "Metadata_ConcLevel", "Metadata_Well", "Metadata_Plate"]].copy()
+        pm2["Metadata_Compound"] = pm2["Metadata_Compound"].str.upper()
+        merged = pm2.merge(merged, on="Metadata_Well", how="inner")
+        feats = [c for c in merged.columns if "Metadata" not in c]
+        z = o_norm.mad_robustize(merged[feats].to_numpy(float), (merged["Metadata_Compound"] == "DMSO").to_numpy())
+        assert list(got.columns) == [c for c in merged.columns if c not in feats] + ["Metadata_Timepoint"] + feats
+        assert list(got["Metadata_Well"]) == list(merged["Metadata_Well"])
+        np.testing.assert_allclose(got[feats].to_numpy(float), z, rtol=1e-9, atol=1e-9)
     with pytest.raises(ValueError, match="no GPU kernel"):
-        nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", "median", False, qc_drop, s3)
+        nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", "sum", False, qc_drop, s3)
 
 
 def test_feature_select_cosine_script(tmp_path, monkeypatch):
