@@ -218,6 +218,10 @@ def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_c
     df = read_csv_from_s3(bucket_data_set, data_set, s3_client)
     chunks = list(_chunks_of(df, num_channels, num_planes))
     plates = [c[0] for c in chunks]
+    if not chunks:                                 # nothing to project: no device, no threads
+        for plate in df['PlateID'].unique():
+            logger.info(f"Plate {plate} finished! Check images in bucket.")
+        return 0
 
     def batches():
         for i in range(0, len(chunks), batch_fields):
