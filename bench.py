@@ -352,67 +352,30 @@ def gpu_arm(args):
         n_chunks -= 1
     slots_per_chunk = n_slots // n_chunks
     chunk_fields = slots_per_chunk * Fb
-    # One header-led block per (chunk, rank): row 0 carries the row count, so the gather is ONE
-    # fixed-size ncclAllGather per chunk and the launching thread never waits for the device
-    # (ips_pack_rows_block -> ips_allgather_blocks -> ips_well_sums_add_blocks).
-    block_rows = chunk_fields * n_max + 1
-    gatherer = plate_mod.BlockGatherer()
-    # The bulk of the gather goes over NVSwitch peer memory with the copy engines (plate.PeerPusher:
-    # every block is stored into every peer's table as soon as it is final, no SM involved); the one
-    # NCCL all-gather that remains (the per-rank row totals, at the end of the plate) is the barrier.
-    # Without CUDA IPC the blocks themselves go through ncclAllGather, chunk by chunk.
-    pusher, push_note = None, "n/a (one rank)"
-    if world > 1 and not args.no_peer_push:
-        try:
-            table = plate_mod.exportable_zeros((n_chunks, world, block_rows, D_row))
-            pusher = plate_mod.PeerPusher(table)
-            push_note = "copy-engine stores into the peers' tables (CUDA IPC over NVLink), one NCCL all-gather of the row totals as barrier"
-        except Exception as e:                                  # IPC not available in this container
-            pusher, push_note = None, "unavailable (%s): ncclAllGather per chunk" % (str(e)[:80])
-    ok_all = torch.tensor([1 if (pusher is not None or world == 1) else 0], device=dev)
-    if dist is not None:
-        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)           # all ranks take the same path
-    if world > 1 and int(ok_all.item()) == 0:
-        if pusher is not None:
-            pusher.close()
-        pusher = None
-        if args.no_peer_push:
-            push_note = "disabled (--no-peer-push): ncclAllGather per chunk"
-    if pusher is None:
-        table = torch.zeros((n_chunks, world, block_rows, D_row), dtype=torch.float32, device=dev)
-    totals = torch.zeros((world, 1, D_row), dtype=torch.float32, device=dev)
+    # One header-led block per (chunk, rank): row 0 carries the row count, so neither side of the
+    # exchange needs a host round trip.  plate.PlateRowExchange packs a chunk's rows on a side stream
+    # and moves the block over NVSwitch peer memory with the copy engines (every block is stored into
+    # every peer's table, no SM involved); the one NCCL all-gather that remains (the per-chunk counts,
+    # at the end of the plate) is the barrier.  Without CUDA IPC the blocks themselves go through
+    # ncclAllGather, chunk by chunk.
+    exchange = plate_mod.PlateRowExchange(n_chunks, chunk_fields, n_max, C_, peer_push=not args.no_peer_push)
+    table, block_rows, push_note = exchange.table, exchange.block_rows, exchange.transport
     well_agg = plate_mod.WellAggregator(n_wells, D_row, device=dev)
-    pack_ws = torch.empty(max(int(capi.call("ips_pack_rows_workspace_bytes", chunk_fields)), 16), dtype=torch.uint8, device=dev)
-    agg_stream = torch.cuda.Stream(device=dev, priority=-1)   # its few CTAs must not queue behind a full fused grid
-    chunk_events = [torch.cuda.Event() for _ in range(n_chunks)]
 
     def gather_chunk(g):
-        """Fields of chunk g are done on the compute stream: pack their rows into this rank's
-        block and all-gather the chunk's blocks on the side stream.  No host synchronisation."""
-        chunk_events[g].record()
-        with torch.cuda.stream(agg_stream):
-            agg_stream.wait_event(chunk_events[g])
-            fs = slice(g * chunk_fields, (g + 1) * chunk_fields)
-            plate_mod.pack_rows_block(plate_ints[fs], plate_flts[fs], plate_n[fs], field_well[fs], table[g, rank],
-                                      field_base=g * chunk_fields, ws=pack_ws)
-            if pusher is not None:
-                pusher.push(table[g, rank])
-            else:
-                gatherer.gather(table[g])
+        """Fields of chunk g are done on the compute stream: pack their rows into this rank's block and
+        send it on its way.  No host synchronisation."""
+        fs = slice(g * chunk_fields, (g + 1) * chunk_fields)
+        exchange.submit(g, plate_ints[fs], plate_flts[fs], plate_n[fs], field_well[fs], field_base=g * chunk_fields)
 
-    def finish_plate():
-        # Per-well sums run after the last field: measured at N = 8, folding them into the side
-        # stream chunk by chunk slowed the field kernels by more (0.755 -> 0.794 ms per launch)
-        # than the shorter tail gained (profiles/README.md).
-        if pusher is not None:
-            with torch.cuda.stream(agg_stream):               # the one NCCL all-gather: row totals + barrier
-                n_here = plate_n.clamp(min=0).sum()
-                totals[rank, 0, 0] = (n_here // 65536).to(torch.float32)
-                totals[rank, 0, 1] = (n_here % 65536).to(torch.float32)
-                gatherer.gather(totals)
-        torch.cuda.current_stream().wait_stream(agg_stream)
+    def finish_plate(ev=None):
+        # Per-well sums run after the last field, over the whole gathered table (every rank sums the
+        # rows of all wells): the blocks of the peers are only known to have landed after the barrier.
+        blocks = exchange.finish()
+        if ev is not None:
+            ev.record()
         well_agg.reset()
-        well_agg.add_blocks(table.view(n_chunks * world, block_rows, D_row))
+        well_agg.add_blocks(blocks)
         return well_agg.finalize()
 
     def aggregate_all():
@@ -454,10 +417,20 @@ def gpu_arm(args):
 
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_steps = torch.cuda.Event(enable_timing=True)
+    t_steps, t_gathered = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # The ranks enter the timed region together ON THE DEVICE: NVML start-up and the barrier's exit differ
+    # by milliseconds between eight processes, and a rank that starts early would carry that skew as a
+    # wait in front of the plate's final barrier.  NVML is therefore initialised before the barrier, and
+    # a stream-ordered all-reduce right in front of t_begin holds every GPU until the last rank has
+    # queued its own.
+    sampler = ClockSampler(local)                               # NVML start-up: before the barrier
+    sync_token = torch.zeros(1, device=dev)
     barrier()
     l0 = capi.launch_count()
-    with ClockSampler(local) as clocks:
+    with sampler as clocks:
+        pushed0 = exchange.pushed_bytes
+        if dist is not None:
+            dist.all_reduce(sync_token)
         t_begin.record()
         chunks_done = 0
         for i in range(args.steps):
@@ -468,12 +441,13 @@ def gpu_arm(args):
         t_steps.record()
         for g in range(chunks_done, n_chunks):
             gather_chunk(g)
-        well_mean_dev, well_count_dev = finish_plate()
+        well_mean_dev, well_count_dev = finish_plate(t_gathered)
         t_end.record()
         barrier()
     launches = capi.launch_count() - l0
+    pushed_last_plate = exchange.pushed_bytes - pushed0
     # ---- content check of the gathered table (outside the timed region) ---------------------
-    counts_all = plate_mod.block_counts(table.view(n_chunks * world, block_rows, D_row)).view(n_chunks, world)
+    counts_all = exchange.counts()
     n_rows = int(counts_all[:, rank].sum().item())
     agg_check = "ok"
     local_rows = int(plate_n.clamp(min=0).sum().item())
@@ -505,6 +479,7 @@ def gpu_arm(args):
             agg_check = "ranks disagree on the gathered per-well means"
     ms_total = t_begin.elapsed_time(t_end)
     ms_aggregate = t_steps.elapsed_time(t_end)
+    ms_exchange_tail = t_steps.elapsed_time(t_gathered)
     k1_all = [e[0].elapsed_time(e[1]) for e in evs]
     k3_all = [e[1].elapsed_time(e[2]) for e in evs]
     k1_ms, k3_ms = float(np.mean(k1_all)), float(np.mean(k3_all))
@@ -708,8 +683,11 @@ def gpu_arm(args):
                                  "remaining fields (counts in block headers, no host sync)" % n_chunks) if world > 1
                                 else "no gather at N=1"),
                             "check": agg_check, "bulk_transport": push_note,
-                            "ms_after_last_step": ms_aggregate, "rows_per_rank": n_rows, "row_bytes": D_row * 4,
+                            "ms_after_last_step": ms_aggregate,
+                            "ms_last_chunk_and_barrier": ms_exchange_tail, "ms_well_sums": ms_aggregate - ms_exchange_tail,
+                            "rows_per_rank": n_rows, "row_bytes": D_row * 4,
                             "gather_bytes_per_rank": n_rows * D_row * 4 if world > 1 else 0,
+                            "bytes_pushed_to_peers_last_plate": pushed_last_plate,
                             "wells": n_wells, "wells_with_rows": int((well_count_dev > 0).sum().item())},
             "cpu_baseline": cpu,
             "e2e_files": e2e_files,
@@ -718,6 +696,7 @@ def gpu_arm(args):
             "objects_last_field": int(n_obj_last[-1]),
         }
         _RESULT_LINE.append(json.dumps(line))
+    exchange.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -731,7 +710,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fused", choices=["fused", "split"],
                     help="fused: one K1+K3 pass per step (ips_field_fused); split: K1 then K3")
-    ap.add_argument("--gather-chunks", type=int, default=10, help="pieces the plate's row all-gather is issued in")
+    ap.add_argument("--gather-chunks", type=int, default=20, help="pieces the plate's row all-gather is issued in")
     ap.add_argument("--batch", type=int, default=16, help="fields per step")
     ap.add_argument("--ring", type=int, default=32, help="distinct device-resident fields")
     ap.add_argument("--e2e-batch", type=int, default=4)

@@ -2,30 +2,35 @@
 // (Normalize_CP_ami.py:126, Pycyto_pertime.py:69-72) -- the consumer of the all-gather.
 //
 // Mean.  rows [N][D] with a well id per row -> per-well float64 means, NaN skipped per column as
-// pandas does (every (well, column) keeps its own count of non-NaN values).  A thread owns one
-// column of a 32-row run; consecutive rows of one well (the common layout: rows arrive grouped by
-// field, fields by well) fold in a register and leave with one float64 atomic per run.  Any
-// number of columns: grid.y walks column tiles of at most 256.
+// pandas does (every (well, column) keeps its own count of non-NaN values).  A CTA takes a tile of
+// subs x rpt consecutive rows; a thread owns one column and every subs-th row of the tile, so the
+// CTA's loads sweep the tile contiguously and a thread has eight independent loads in flight.
+// Rows of one well (the common layout: rows arrive grouped by field, fields by well) fold in
+// registers and leave with one atomic per (thread, well, class).  Any number of columns: grid.y
+// walks column tiles of at most 256.  Header-led block tables (ips_pack_rows_block) put one table
+// block on grid.z: the header is read once per CTA and the CTAs behind the block's count exit.
 //
-// Float32 rows are summed EXACTLY, hence independently of the order in which runs, chunks and
-// ranks deliver them: a float32 is an integer multiple of 2^(E-150) below 2^(E-126) (E = biased
-// exponent), so values whose exponents share E >> 3 -- a "class" of 8 binades -- add without
-// rounding in float64 for up to 2^22 values per (well, column, class).  There is one float64
-// accumulator per class (32 of them); only the final sum over the classes, taken in ascending
-// order by one thread, rounds.  The per-well means of a gathered table are therefore bit-identical
-// to those of the local rows (bench.py `aggregation.check`), whatever the atomics' order.
+// Float32 rows are summed EXACTLY in 64-bit integers, one per exponent class (wellmean_exact.cuh),
+// hence independently of the order in which threads, chunks and ranks deliver them; only the final
+// sum over the 32 classes, taken in ascending order by one thread, rounds.  The per-well means of a
+// gathered table are therefore bit-identical to those of the local rows (bench.py
+// `aggregation.check`), whatever the atomics' order.  +-inf are kept as two flag bits per (well,
+// column): the mean is +-inf, or NaN when both occur, as in IEEE addition.
 // Float64 rows (the script tables) use one accumulator and ordinary float64 atomics.
 //
 // Median.  One 256-thread block per (well, 32-column tile) over rows grouped by well through a
 // permutation: exact k-th smallest by 8 x 8-bit radix select on order-preserving 64-bit keys,
 // both middle ranks, NaN skipped.
 #include "ips_common.cuh"
+#include "wellmean_exact.cuh"
 
 namespace ips {
 
-constexpr int WM_ROWS = 32;        // rows per thread run
 constexpr int WM_THREADS = 256;
-constexpr int WM_CLASSES = 32;     // exponent classes of the exact float32 accumulation
+constexpr int WM_CLASSES = WMX_CLASSES;   // exponent classes of the exact float32 accumulation
+constexpr int WM_UNROLL = 8;              // independent loads per thread
+constexpr int WM_RPT_SMALL = 32, WM_RPT_LARGE = 64;   // rows per thread (tile = subs x rpt rows)
+constexpr int WM_TILE_MAX = 2048;         // rows per tile (their well ids are staged in shared memory)
 
 __global__ void well_zero_kernel(double* sums, int* counts, size_t n_sums, size_t n_counts) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,82 +38,181 @@ __global__ void well_zero_kernel(double* sums, int* counts, size_t n_sums, size_
   if (i < n_counts) counts[i] = 0;
 }
 
-// Well id of table row r.  Plain mode: well[r].  Header mode (well == nullptr): the table is a
-// sequence of blocks of `block_rows` rows whose first row is a header carrying the number of
-// valid rows that follow (two 32-bit words); the well id is column 0 of the row itself.
-template <typename T>
-__device__ __forceinline__ int wm_row_well(const T* __restrict__ rows, const int32_t* __restrict__ well,
-                                           long long r, int D, long long block_rows) {
-  if (well != nullptr) return well[r];
-  const long long b = r / block_rows, k = r - b * block_rows;
-  if (k == 0) return -1;
-  const uint32_t* h = reinterpret_cast<const uint32_t*>(rows + (size_t)b * block_rows * D);
-  const long long n = (long long)h[0] | ((long long)h[1] << 32);
-  return k <= n ? (int)rows[(size_t)r * D] : -1;
+struct WmOut {
+  double* sums;      // [n_wells][D][K] float64, or the same bytes as int64 class sums
+  int* colcnt;       // [n_wells][D] non-NaN values
+  int* rowcnt;       // [n_wells]
+  int* flags;        // [n_wells][D] bit 0: +inf seen, bit 1: -inf seen (exact path only)
+};
+
+// What a thread carries for the well it is in.  Exact path: the sums of the two exponent classes
+// seen last (a column's values rarely straddle more) as float64 -- at most 64 values of one class,
+// i.e. integers below 2^37 in units of the class: exact -- turned into the integer multiple of the
+// class unit when they leave; rows taken, NaNs skipped, inf flags.
+struct WmExact {
+  double a0 = 0.0, a1 = 0.0;
+  int c0 = -1, c1 = -1, k = 0, nan = 0, inf = 0;
+};
+struct WmPlain {
+  double acc = 0.0;
+  int k = 0, nan = 0;
+};
+
+__device__ __forceinline__ unsigned long long* wm_class_sums(const WmOut& o, int w, int D, int d) {
+  return reinterpret_cast<unsigned long long*>(o.sums) + ((size_t)w * D + d) * WM_CLASSES;
+}
+// a class sum held as float64 -> its (exact) integer multiple of the class unit
+__device__ __forceinline__ unsigned long long wm_units(double a, int c) {
+  return (unsigned long long)__double2ll_rn(a * wmx_pow2(-wmx_unit_exp(c)));
+}
+__device__ __forceinline__ void wm_flush(const WmExact& t, const WmOut& o, int w, int D, int d) {
+  unsigned long long* s = wm_class_sums(o, w, D, d);
+  if (t.c0 >= 0 && t.a0 != 0.0) atomicAdd(s + t.c0, wm_units(t.a0, t.c0));
+  if (t.c1 >= 0 && t.a1 != 0.0) atomicAdd(s + t.c1, wm_units(t.a1, t.c1));
+  if (t.k > t.nan) atomicAdd(&o.colcnt[(size_t)w * D + d], t.k - t.nan);
+  if (t.inf) atomicOr(&o.flags[(size_t)w * D + d], t.inf);
+  if (d == 0) atomicAdd(&o.rowcnt[w], t.k);
+}
+__device__ __forceinline__ void wm_flush(const WmPlain& t, const WmOut& o, int w, int D, int d) {
+  if (t.k > t.nan) {
+    atomicAdd(&o.sums[(size_t)w * D + d], t.acc);
+    atomicAdd(&o.colcnt[(size_t)w * D + d], t.k - t.nan);
+  }
+  if (d == 0) atomicAdd(&o.rowcnt[w], t.k);
 }
 
-// Thread (sub, dl): column blockIdx.y * cols + dl of the 32-row run `sub` of the block.  The
-// threads of one run read consecutive values of a row (coalesced).
-template <typename T, bool EXACT>
+// One value of the thread's column.  Hot path: a float32 of one of the two classes the thread holds,
+// widened and added.  Everything else (zero, NaN, inf, the top class, a third class) takes the branch.
+__device__ __forceinline__ void wm_take(WmExact& t, float v, const WmOut& o, int w, int D, int d) {
+  ++t.k;
+  const uint32_t bits = __float_as_uint(v);
+  const int c = (int)((bits >> 26) & 31u);
+  const double x = (double)v;
+  if (c == t.c0) t.a0 += x;
+  else if (c == t.c1) t.a1 += x;
+  else {
+    const uint32_t absb = bits & 0x7fffffffu;
+    if (absb == 0u) return;                                   // +-0
+    if (absb >= 0x7f800000u) {                                // NaN: skipped, not counted; inf: flagged
+      if (absb > 0x7f800000u) ++t.nan;
+      else t.inf |= (bits >> 31) ? 2 : 1;
+      return;
+    }
+    if (c == WM_CLASSES - 1) {                                // never held in a slot: NaN and inf would match it
+      atomicAdd(wm_class_sums(o, w, D, d) + c, wm_units(x, c));
+      return;
+    }
+    if (t.c1 >= 0 && t.a1 != 0.0) atomicAdd(wm_class_sums(o, w, D, d) + t.c1, wm_units(t.a1, t.c1));
+    t.c1 = t.c0; t.a1 = t.a0;                                 // a third class: the older one leaves
+    t.c0 = c; t.a0 = x;
+  }
+}
+__device__ __forceinline__ void wm_take(WmPlain& t, double v, const WmOut&, int, int, int) {
+  ++t.k;
+  if (v == v) t.acc += v;
+  else ++t.nan;
+}
+
+// The rows of one thread: local rows sub, sub + subs, ... of the tile (`mine` of them), column d.
+// UNIFORM: every row of the tile belongs to well w0 (checked by the CTA) -- no per-row test.
+template <typename T, typename Run, bool UNIFORM>
+__device__ __forceinline__ void wm_thread_rows(const T* __restrict__ pv, const int* s_well, int mine, int stride,
+                                               int subs, int w0, const WmOut& out, int D, int d, int n_wells) {
+  Run run;
+  int cur = UNIFORM ? w0 : -2;                              // -2: no well yet
+  auto take = [&](T v, int w) {
+    if (!UNIFORM && w != cur) {
+      if (w < 0 || w >= n_wells) return;                    // rows without a well (id out of range) are dropped
+      if (cur >= 0) wm_flush(run, out, cur, D, d);
+      cur = w;
+      run = Run();
+    }
+    wm_take(run, v, out, cur, D, d);
+  };
+  // batches of WM_UNROLL rows, the next batch's loads issued before the current one is summed
+  const T* p = pv;                                          // walks the thread's rows: one add per load
+  T nx[WM_UNROLL];
+  const int full = mine / WM_UNROLL;
+  if (full > 0) {
+#pragma unroll
+    for (int j = 0; j < WM_UNROLL; ++j, p += stride) nx[j] = *p;
+  }
+  for (int b = 0; b < full; ++b) {
+    T v[WM_UNROLL];
+#pragma unroll
+    for (int j = 0; j < WM_UNROLL; ++j) v[j] = nx[j];
+    if (b + 1 < full) {
+#pragma unroll
+      for (int j = 0; j < WM_UNROLL; ++j, p += stride) nx[j] = *p;
+    }
+#pragma unroll
+    for (int j = 0; j < WM_UNROLL; ++j) take(v[j], UNIFORM ? w0 : s_well[(b * WM_UNROLL + j) * subs]);
+  }
+  for (int i = full * WM_UNROLL; i < mine; ++i, p += stride) take(*p, UNIFORM ? w0 : s_well[i * subs]);
+  if (cur >= 0) wm_flush(run, out, cur, D, d);
+}
+
+// CTA = tile of subs * rpt consecutive rows (at most WM_TILE_MAX); thread (sub, dl) = column
+// blockIdx.y * cols + dl.  well != nullptr: one table of N rows with a well id per row.
+// well == nullptr (float32 only): table block blockIdx.z of `block_rows` rows, row 0 a header
+// carrying the number of valid rows that follow (two 32-bit words), the well id of a row its
+// column 0.  The tile's well ids are staged in shared memory once; a tile inside one well (the
+// rule: a well is thousands of consecutive rows) runs without per-row tests.
+template <typename T, typename Run>
 __global__ void __launch_bounds__(WM_THREADS)
-well_accumulate_kernel(const T* __restrict__ rows, const int32_t* __restrict__ well, double* __restrict__ sums,
-                       int* __restrict__ colcnt, int* __restrict__ rowcnt, long long N, int D, int n_wells,
-                       int cols, int subs, long long block_rows) {
-  constexpr int K = EXACT ? WM_CLASSES : 1;
+well_accumulate_kernel(const T* __restrict__ rows, const int32_t* __restrict__ well, WmOut out, long long N, int D,
+                       int n_wells, int cols, int subs, int rpt, long long block_rows) {
+  __shared__ int s_well[WM_TILE_MAX];
+  const T* seg = rows;
+  long long n = N;
+  if (well == nullptr) {
+    seg += (size_t)blockIdx.z * block_rows * D;
+    const uint32_t* h = reinterpret_cast<const uint32_t*>(seg);
+    n = (long long)h[0] | ((long long)h[1] << 32);
+    if (n > block_rows - 1) n = block_rows - 1;            // a damaged header cannot lead past its block
+    seg += D;
+  }
+  const int tile = subs * rpt;
+  const long long R0 = (long long)blockIdx.x * tile;
+  if (R0 >= n) return;                                      // the whole CTA: behind the block's count
+  const int span = n - R0 < (long long)tile ? (int)(n - R0) : tile;
+  const T* tseg = seg + (size_t)R0 * D;
+  const int32_t* twell = well != nullptr ? well + R0 : nullptr;
+  const int w0 = twell != nullptr ? twell[0] : (int)tseg[0];
+  bool same = w0 >= 0 && w0 < n_wells;
+  for (int r = threadIdx.x; r < span; r += WM_THREADS) {
+    const int w = twell != nullptr ? twell[r] : (int)tseg[(size_t)r * D];
+    s_well[r] = w;
+    same = same && w == w0;
+  }
+  const bool uniform = __syncthreads_and(same);
   const int sub = threadIdx.x / cols, dl = threadIdx.x - sub * cols;
-  if (sub >= subs) return;
   const int d = blockIdx.y * cols + dl;
-  if (d >= D) return;
-  const long long r0 = ((long long)blockIdx.x * subs + sub) * WM_ROWS;
-  if (r0 >= N) return;
-  const long long r1 = r0 + WM_ROWS < N ? r0 + WM_ROWS : N;
-  int cur = -1, cls = 0, cnt = 0, nrow = 0;
-  bool pending = false;
-  double acc = 0.0;
-  for (long long r = r0; r < r1; ++r) {
-    const int w = wm_row_well(rows, well, r, D, block_rows);
-    if (w < 0 || w >= n_wells) continue;   // rows without a well (id out of range) are dropped
-    if (w != cur) {
-      if (cur >= 0) {
-        if (pending) atomicAdd(&sums[((size_t)cur * D + d) * K + cls], acc);
-        if (cnt) atomicAdd(&colcnt[(size_t)cur * D + d], cnt);
-        if (d == 0) atomicAdd(&rowcnt[cur], nrow);
-      }
-      cur = w; acc = 0.0; cnt = 0; nrow = 0; pending = false;
-    }
-    ++nrow;
-    const T v = rows[(size_t)r * D + d];
-    if (v == v) {
-      if (EXACT) {
-        const int k = (int)((__float_as_uint((float)v) >> 26) & 31u);
-        if (pending && k != cls) {
-          atomicAdd(&sums[((size_t)cur * D + d) * K + cls], acc);
-          acc = 0.0;
-        }
-        cls = k;
-      }
-      acc += (double)v;
-      ++cnt;
-      pending = true;
-    }
-  }
-  if (cur >= 0) {
-    if (pending) atomicAdd(&sums[((size_t)cur * D + d) * K + cls], acc);
-    if (cnt) atomicAdd(&colcnt[(size_t)cur * D + d], cnt);
-    if (d == 0) atomicAdd(&rowcnt[cur], nrow);
-  }
+  if (sub >= subs || d >= D || sub >= span) return;
+  const int mine = (span - sub + subs - 1) / subs;
+  const T* pv = tseg + (size_t)sub * D + d;
+  if (uniform) wm_thread_rows<T, Run, true>(pv, s_well + sub, mine, subs * D, subs, w0, out, D, d, n_wells);
+  else wm_thread_rows<T, Run, false>(pv, s_well + sub, mine, subs * D, subs, w0, out, D, d, n_wells);
 }
 
 __global__ void well_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ colcnt,
-                                     const int* __restrict__ rowcnt, double* __restrict__ mean_out,
-                                     int32_t* __restrict__ count_out, int n_wells, int D, int K) {
+                                     const int* __restrict__ rowcnt, const int* __restrict__ flags,
+                                     double* __restrict__ mean_out, int32_t* __restrict__ count_out, int n_wells, int D,
+                                     int exact) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n_wells * D) return;
   const int w = (int)(i / D);
-  double s = 0.0;
-  for (int k = 0; k < K; ++k) s += sums[i * K + k];      // ascending exponent class: small terms first
+  const double nan = __longlong_as_double(0x7ff8000000000000ll), inf = __longlong_as_double(0x7ff0000000000000ll);
+  double s;
+  if (exact) {
+    s = wmx_total(reinterpret_cast<const long long*>(sums) + i * WM_CLASSES);
+    const int f = flags[i];
+    if (f) s = f == 1 ? inf : f == 2 ? -inf : nan;
+  } else {
+    s = sums[i];
+  }
   const int c = colcnt[i];
-  mean_out[i] = c > 0 ? s / (double)c : __longlong_as_double(0x7ff8000000000000ll);
+  mean_out[i] = c > 0 ? s / (double)c : nan;
   if (i % D == 0) count_out[w] = rowcnt[w];
 }
 
@@ -116,17 +220,17 @@ static size_t wm_sums_bytes(int n_wells, int D) { return round_up((size_t)n_well
 static size_t wm_colcnt_bytes(int n_wells, int D) { return round_up((size_t)n_wells * D * sizeof(int), 256); }
 static size_t wm_rowcnt_bytes(int n_wells) { return round_up((size_t)n_wells * sizeof(int), 256); }
 
-struct WmWs {
-  double* sums;
-  int* colcnt;
-  int* rowcnt;
-};
-static WmWs wm_carve(void* ws, int n_wells, int D) {
+// workspace: sums | colcnt | flags | rowcnt (the three integer arrays are adjacent: one zero fill)
+static WmOut wm_carve(void* ws, int n_wells, int D) {
   char* p = reinterpret_cast<char*>(ws);
-  WmWs w;
+  WmOut w;
   w.sums = reinterpret_cast<double*>(p);
-  w.colcnt = reinterpret_cast<int*>(p + wm_sums_bytes(n_wells, D));
-  w.rowcnt = reinterpret_cast<int*>(p + wm_sums_bytes(n_wells, D) + wm_colcnt_bytes(n_wells, D));
+  p += wm_sums_bytes(n_wells, D);
+  w.colcnt = reinterpret_cast<int*>(p);
+  p += wm_colcnt_bytes(n_wells, D);
+  w.flags = reinterpret_cast<int*>(p);
+  p += wm_colcnt_bytes(n_wells, D);
+  w.rowcnt = reinterpret_cast<int*>(p);
   return w;
 }
 
@@ -217,7 +321,7 @@ using namespace ips;
 
 extern "C" size_t ips_well_mean_workspace_bytes(int n_wells, int D) {
   if (n_wells <= 0 || D <= 0) return 0;
-  return wm_sums_bytes(n_wells, D) + wm_colcnt_bytes(n_wells, D) + wm_rowcnt_bytes(n_wells);
+  return wm_sums_bytes(n_wells, D) + 2 * wm_colcnt_bytes(n_wells, D) + wm_rowcnt_bytes(n_wells);
 }
 
 static int wm_check(const void* ws, size_t ws_bytes, int D, int n_wells, const char* who) {
@@ -235,26 +339,31 @@ extern "C" int ips_well_sums_reset(void* ws, size_t ws_bytes, int D, int n_wells
   const int rc = wm_check(ws, ws_bytes, D, n_wells, "ips_well_sums_reset");
   if (rc != IPS_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const WmWs w = wm_carve(ws, n_wells, D);
+  const WmOut w = wm_carve(ws, n_wells, D);
   const size_t n_sums = (size_t)n_wells * D * WM_CLASSES;
-  // colcnt and rowcnt are adjacent up to padding: zero the whole integer tail
-  const size_t n_counts = (wm_colcnt_bytes(n_wells, D) + wm_rowcnt_bytes(n_wells)) / sizeof(int);
+  // colcnt, flags and rowcnt are adjacent up to padding: zero the whole integer tail
+  const size_t n_counts = (2 * wm_colcnt_bytes(n_wells, D) + wm_rowcnt_bytes(n_wells)) / sizeof(int);
   well_zero_kernel<<<(unsigned)((n_sums + 255) / 256), 256, 0, st>>>(w.sums, w.colcnt, n_sums, n_counts);
   IPS_LAUNCH_OK("well_zero_kernel");
   return IPS_OK;
 }
 
-template <typename T, bool EXACT>
-static int wm_add(const T* rows, const int32_t* well, int64_t N, void* ws, int D, int n_wells, long long block_rows,
-                  cudaStream_t st) {
-  const WmWs w = wm_carve(ws, n_wells, D);
+// n_seg table blocks of seg_rows rows each (header mode, well == nullptr), or one table of N rows.
+template <typename T, typename Run>
+static int wm_add(const T* rows, const int32_t* well, int64_t N, int64_t n_seg, void* ws, int D, int n_wells,
+                  long long block_rows, cudaStream_t st) {
+  const WmOut w = wm_carve(ws, n_wells, D);
   const int cols = D < WM_THREADS ? D : WM_THREADS, subs = WM_THREADS / cols;
-  const long long rows_per_block = (long long)subs * WM_ROWS;
-  const long long blocks = (N + rows_per_block - 1) / rows_per_block;
+  const long long seg_rows = well != nullptr ? (long long)N : block_rows - 1;
+  int rpt = seg_rows >= (1 << 14) ? WM_RPT_LARGE : WM_RPT_SMALL;
+  if (rpt * subs > WM_TILE_MAX) rpt = WM_TILE_MAX / subs;   // narrow tables: subs up to 256
+  const long long tile = (long long)subs * rpt;
+  const long long blocks = (seg_rows + tile - 1) / tile;
   const int tiles = (D + cols - 1) / cols;
-  if (blocks > 0x7fffffffLL || tiles > 65535) IPS_FAIL(IPS_ERR_BAD_SHAPE, "well sums: table too large for one call");
-  well_accumulate_kernel<T, EXACT><<<dim3((unsigned)blocks, (unsigned)tiles), WM_THREADS, 0, st>>>(
-      rows, well, w.sums, w.colcnt, w.rowcnt, N, D, n_wells, cols, subs, block_rows);
+  if (blocks > 0x7fffffffLL || tiles > 65535 || n_seg > 65535)
+    IPS_FAIL(IPS_ERR_BAD_SHAPE, "well sums: table too large for one call");
+  well_accumulate_kernel<T, Run><<<dim3((unsigned)blocks, (unsigned)tiles, (unsigned)n_seg), WM_THREADS, 0, st>>>(
+      rows, well, w, (long long)N, D, n_wells, cols, subs, rpt, block_rows);
   IPS_LAUNCH_OK("well_accumulate_kernel");
   return IPS_OK;
 }
@@ -266,7 +375,7 @@ extern "C" int ips_well_sums_add(const float* rows, const int32_t* well, int64_t
   if (N < 0) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_sums_add: negative row count");
   if (N == 0) return IPS_OK;
   if (!rows || !well) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_sums_add: NULL rows");
-  return wm_add<float, true>(rows, well, N, ws, D, n_wells, 0, reinterpret_cast<cudaStream_t>(stream));
+  return wm_add<float, WmExact>(rows, well, N, 1, ws, D, n_wells, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ips_well_sums_add_blocks(const float* table, int64_t n_blocks, int64_t block_rows, void* ws,
@@ -277,8 +386,21 @@ extern "C" int ips_well_sums_add_blocks(const float* table, int64_t n_blocks, in
   if (D < 2) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_sums_add_blocks: header rows need D >= 2");
   if (n_blocks == 0 || block_rows == 1) return IPS_OK;
   if (!table) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_sums_add_blocks: NULL table");
-  return wm_add<float, true>(table, nullptr, n_blocks * block_rows, ws, D, n_wells, block_rows,
-                             reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // grid.z carries the table blocks, at most 65535 per launch
+  for (int64_t b0 = 0; b0 < n_blocks; b0 += 65535) {
+    const int64_t nb = n_blocks - b0 < 65535 ? n_blocks - b0 : 65535;
+    const int rc2 = wm_add<float, WmExact>(table + (size_t)b0 * block_rows * D, nullptr, 0, nb, ws, D, n_wells, block_rows, st);
+    if (rc2 != IPS_OK) return rc2;
+  }
+  return IPS_OK;
+}
+
+static void wm_finalize(const WmOut& w, double* mean_out, int32_t* count_out, int D, int n_wells, int exact,
+                        cudaStream_t st) {
+  const size_t n = (size_t)n_wells * D;
+  well_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.sums, w.colcnt, w.rowcnt, w.flags, mean_out,
+                                                                    count_out, n_wells, D, exact);
 }
 
 extern "C" int ips_well_sums_finalize(const void* ws, size_t ws_bytes, double* mean_out, int32_t* count_out, int D,
@@ -286,11 +408,8 @@ extern "C" int ips_well_sums_finalize(const void* ws, size_t ws_bytes, double* m
   const int rc = wm_check(ws, ws_bytes, D, n_wells, "ips_well_sums_finalize");
   if (rc != IPS_OK) return rc;
   if (!mean_out || !count_out) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_sums_finalize: NULL output");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const WmWs w = wm_carve(const_cast<void*>(ws), n_wells, D);
-  const size_t n = (size_t)n_wells * D;
-  well_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.sums, w.colcnt, w.rowcnt, mean_out, count_out,
-                                                                    n_wells, D, WM_CLASSES);
+  wm_finalize(wm_carve(const_cast<void*>(ws), n_wells, D), mean_out, count_out, D, n_wells, 1,
+              reinterpret_cast<cudaStream_t>(stream));
   IPS_LAUNCH_OK("well_finalize_kernel");
   return IPS_OK;
 }
@@ -307,27 +426,18 @@ extern "C" int ips_well_mean(const float* rows, const int32_t* well, double* mea
 extern "C" int ips_well_mean_f64(const double* rows, const int32_t* well, double* mean_out, int32_t* count_out,
                                  int64_t N, int D, int n_wells, void* ws, size_t ws_bytes, ips_stream_t stream) {
   if (N < 0) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_mean_f64: negative row count");
+  if (!mean_out || !count_out) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_mean_f64: NULL output");
   int rc = ips_well_sums_reset(ws, ws_bytes, D, n_wells, stream);
   if (rc != IPS_OK) return rc;
   if (N > 0) {
     if (!rows || !well) IPS_FAIL(IPS_ERR_BAD_ARG, "ips_well_mean_f64: NULL rows");
-    // one accumulator per (well, column): class 0 of the same layout, the other classes stay zero
-    const WmWs w = wm_carve(ws, n_wells, D);
-    const int cols = D < WM_THREADS ? D : WM_THREADS, subs = WM_THREADS / cols;
-    const long long rows_per_block = (long long)subs * WM_ROWS;
-    const long long blocks = (N + rows_per_block - 1) / rows_per_block;
-    const int tiles = (D + cols - 1) / cols;
-    if (blocks > 0x7fffffffLL || tiles > 65535) IPS_FAIL(IPS_ERR_BAD_SHAPE, "ips_well_mean_f64: table too large for one call");
-    well_accumulate_kernel<double, false><<<dim3((unsigned)blocks, (unsigned)tiles), WM_THREADS, 0,
-                                            reinterpret_cast<cudaStream_t>(stream)>>>(
-        rows, well, w.sums, w.colcnt, w.rowcnt, N, D, n_wells, cols, subs, 0);
-    IPS_LAUNCH_OK("well_accumulate_kernel");
-    well_finalize_kernel<<<(unsigned)(((size_t)n_wells * D + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        w.sums, w.colcnt, w.rowcnt, mean_out, count_out, n_wells, D, 1);
-    IPS_LAUNCH_OK("well_finalize_kernel");
-    return IPS_OK;
+    // one float64 accumulator per (well, column): the first n_wells * D words of the same workspace
+    rc = wm_add<double, WmPlain>(rows, well, N, 1, ws, D, n_wells, 0, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != IPS_OK) return rc;
   }
-  return ips_well_sums_finalize(ws, ws_bytes, mean_out, count_out, D, n_wells, stream);
+  wm_finalize(wm_carve(ws, n_wells, D), mean_out, count_out, D, n_wells, 0, reinterpret_cast<cudaStream_t>(stream));
+  IPS_LAUNCH_OK("well_finalize_kernel");
+  return IPS_OK;
 }
 
 extern "C" int ips_well_median_f64(const double* rows, const int64_t* perm, const int64_t* offsets, double* median_out,

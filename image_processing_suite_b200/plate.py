@@ -235,6 +235,136 @@ class PeerPusher:
             self._h = None
 
 
+class PlateRowExchange:
+    """The plate's one all-gather as the rank's fields are finished: object rows leave chunk by chunk
+    while the remaining fields are processed, and ``finish`` returns the gathered table.
+
+    ``table`` [n_chunks][world][block_rows][D] float32 of header-led blocks (``pack_rows_block``),
+    block_rows = chunk_fields * n_max + 1.  ``submit(g, ...)`` packs the rows of chunk ``g`` behind
+    their count and moves the block on a high-priority side stream, without ever blocking the
+    launching thread on work it has just queued:
+
+    * peer push (the default where CUDA IPC works): copy-engine stores into every peer's table
+      (``PeerPusher``).  The copy of chunk ``g`` is issued one ``submit`` later; if its header -- read
+      back to page-locked memory behind the pack -- has arrived by then, only the rows that exist
+      travel (a field holds fewer objects than ``n_max``), otherwise the block goes at capacity
+      (``exact_push="wait"`` waits for the header instead; ``False`` pushes at capacity at once).  The
+      last chunk goes at capacity from ``finish``, which adds ONE small NCCL all-gather (the per-chunk
+      counts of every rank): queued behind this rank's pushes, complete when every rank's has started
+      -- the barrier that publishes the pushes.
+    * otherwise one fixed-size ``ncclAllGather`` per chunk (``BlockGatherer``).
+
+    All ranks take the same path (agreed with one all-reduce at construction).  One rank: the rows are
+    only packed.  Nothing here synchronises with the device except ``counts()``.
+    """
+
+    def __init__(self, n_chunks, chunk_fields, n_max, channels, group=None, peer_push=True, exact_push=True,
+                 device=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        live = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if live else 0
+        self.world = dist.get_world_size(group) if live else 1
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_chunks, self.chunk_fields, self.n_max = int(n_chunks), int(chunk_fields), int(n_max)
+        self.D = 10 + 5 * int(channels)
+        self.block_rows = self.chunk_fields * self.n_max + 1
+        shape = (self.n_chunks, self.world, self.block_rows, self.D)
+        self.pusher, self.transport = None, "n/a (one rank)"
+        self.table = None
+        with torch.cuda.device(self.dev):
+            if self.world > 1 and peer_push:
+                try:
+                    self.table = exportable_zeros(shape)
+                    self.pusher = PeerPusher(self.table, group)
+                    self.transport = ("copy-engine stores into the peers' tables (CUDA IPC over NVLink), "
+                                      "one NCCL all-gather of the chunk counts as barrier")
+                except Exception as e:                          # IPC not available in this container
+                    self.pusher, self.table = None, None
+                    self.transport = "peer push unavailable (%s): ncclAllGather per chunk" % (str(e)[:80])
+            if self.world > 1:
+                ok = torch.tensor([1 if self.pusher is not None else 0], device=self.dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 0 and self.pusher is not None:
+                    self.pusher.close()
+                    self.pusher, self.table = None, None
+                    self.transport = "peer push unavailable on another rank: ncclAllGather per chunk"
+                if self.pusher is None and not peer_push:
+                    self.transport = "ncclAllGather per chunk (peer push disabled)"
+            if self.table is None:
+                self.table = torch.zeros(shape, dtype=torch.float32, device=self.dev)
+            self.gatherer = BlockGatherer(group) if self.world > 1 else None
+            self.exact_push = exact_push if self.pusher is not None else False
+            self.chunk_counts = torch.zeros((self.world, self.n_chunks, 2), dtype=torch.float32, device=self.dev)
+            self.stream = torch.cuda.Stream(device=self.dev, priority=-1)   # its few CTAs must not queue behind a full grid
+            self._done = [torch.cuda.Event() for _ in range(self.n_chunks)]
+            self._hdr_host = torch.zeros((self.n_chunks, 2), dtype=torch.int32).pin_memory()
+            self._hdr_ready = [torch.cuda.Event() for _ in range(self.n_chunks)]
+            self._pending = None
+            self.pushed_bytes = 0
+            n = int(capi.call("ips_pack_rows_workspace_bytes", self.chunk_fields))
+            self._ws = torch.empty(max(n, 16), dtype=torch.uint8, device=self.dev)
+
+    def _push(self, g, exact):
+        blk = self.table[g, self.rank]
+        if exact and (self.exact_push == "wait" or self._hdr_ready[g].query()):
+            self._hdr_ready[g].synchronize()
+            n = (int(self._hdr_host[g, 0]) & 0xffffffff) | (int(self._hdr_host[g, 1]) << 32)
+            blk = blk[:min(max(n, 0), self.block_rows - 1) + 1]
+        self.pushed_bytes += blk.numel() * 4 * (self.world - 1)
+        self.pusher.push(blk)
+
+    def submit(self, g, ints, flts, n_objects, field_well, field_base=0):
+        """The padded rows of chunk ``g``'s fields are final on the current stream: pack and move them."""
+        if not (0 <= g < self.n_chunks) or ints.shape[0] != self.chunk_fields or ints.shape[1] != self.n_max:
+            raise ValueError("chunk %d with %s rows does not fit the exchange" % (g, tuple(ints.shape[:2])))
+        self._done[g].record()
+        with torch.cuda.stream(self.stream):
+            if self._pending is not None:                       # packed one submit ago: its header is (most likely) here
+                self._push(self._pending, True)
+                self._pending = None
+            self.stream.wait_event(self._done[g])
+            pack_rows_block(ints, flts, n_objects, field_well, self.table[g, self.rank], field_base=field_base, ws=self._ws)
+            if self.pusher is not None:
+                if self.exact_push:
+                    self._hdr_host[g].copy_(self.table[g, self.rank, 0, :2].view(torch.int32), non_blocking=True)
+                    self._hdr_ready[g].record()
+                    self._pending = g
+                else:
+                    self._push(g, False)
+            elif self.gatherer is not None:
+                self.gatherer.gather(self.table[g])
+
+    def finish(self):
+        """Everything submitted is on every rank when the current stream reaches this point.
+        Returns the table as [n_chunks * world][block_rows][D] (``WellAggregator.add_blocks``)."""
+        if self.world > 1:
+            with torch.cuda.stream(self.stream):
+                if self._pending is not None:
+                    self._push(self._pending, False)            # at capacity: no wait for its header
+                    self._pending = None
+                if self.pusher is not None:
+                    self.chunk_counts[self.rank].copy_(self.table[:, self.rank, 0, :2])
+                    self.gatherer.gather(self.chunk_counts)
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+        return self.blocks()
+
+    def blocks(self):
+        return self.table.view(self.n_chunks * self.world, self.block_rows, self.D)
+
+    def counts(self):
+        """Row counts [n_chunks][world] (int64, device) from the headers of the gathered table."""
+        return block_counts(self.blocks()).view(self.n_chunks, self.world)
+
+    def close(self):
+        if self.pusher is not None:
+            self.pusher.close()
+            self.pusher = None
+        if self.gatherer is not None:
+            self.gatherer.close()
+            self.gatherer = None
+
+
 def _make_comm(dist, group, rank, world):
     n = int(capi.call("ips_comm_unique_id_bytes"))
     buf = (C.c_char * n)()

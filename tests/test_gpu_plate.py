@@ -177,3 +177,106 @@ def test_peer_push_gather_two_gpus(tmp_path):
     s.close()
     mp.spawn(_push_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _exchange_worker(rank, world, port, tmp):
+    import os
+    import torch
+    import torch.distributed as dist
+    from image_processing_suite_b200 import plate
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        n_chunks, cf, n_max, C = 4, 3, 25, 2
+        nf = 2 + 5 * C
+        D = 8 + nf
+        results = {}
+        for mode in ("wait", True, False):
+            ex = plate.PlateRowExchange(n_chunks, cf, n_max, C, exact_push=mode)
+            assert ex.pusher is not None, ex.transport
+            for rep in range(2):                                   # the second plate overwrites the first
+                rng = np.random.default_rng(900 + 10 * rank + rep)
+                n_obj = rng.integers(0, n_max + 1, (n_chunks, cf)).astype(np.int32)
+                ints = rng.integers(0, 400, (n_chunks, cf, n_max, 6)).astype(np.int32)
+                flts = rng.normal(5.0, 2.0, (n_chunks, cf, n_max, nf)).astype(np.float32)
+                wells = ((np.arange(n_chunks * cf, dtype=np.int32) // 2) * world + rank).reshape(n_chunks, cf)
+                before = ex.pushed_bytes
+                for g in range(n_chunks):
+                    ex.submit(g, dev(ints[g]), dev(flts[g]), dev(n_obj[g]), dev(wells[g]), field_base=g * cf)
+                blocks = ex.finish()
+                agg = plate.WellAggregator(n_chunks * cf * world, D)
+                agg.add_blocks(blocks)
+                mean, count = agg.finalize()
+                torch.cuda.synchronize()
+                counts = ex.counts().cpu().numpy()
+                assert counts[:, rank].tolist() == n_obj.sum(1).tolist()
+                pushed = ex.pushed_bytes - before
+                cap = n_chunks * ex.block_rows * D * 4 * (world - 1)
+                if mode == "wait":                                  # all but the last chunk travel at their size
+                    want = (sum(int(c) + 1 for c in n_obj.sum(1)[:-1]) + ex.block_rows) * D * 4 * (world - 1)
+                    assert pushed == want < cap
+                elif mode is False:
+                    assert pushed == cap
+                # the gathered chunk counts (the barrier's payload) are the headers of the table
+                cc = ex.chunk_counts.cpu().view(torch.int32)[:, :, 0].numpy().T
+                np.testing.assert_array_equal(cc, counts)
+                valid = [blocks[b, 1:1 + int(c)].cpu() for b, c in enumerate(counts.reshape(-1))]
+                results[(str(mode), rep)] = {"rows": valid, "mean": mean.cpu(), "count": count.cpu()}
+            ex.close()
+        torch.save(results, os.path.join(tmp, f"x{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_plate_row_exchange_two_gpus(tmp_path):
+    """plate.PlateRowExchange (what bench.py drives at N > 1): ragged chunks packed, pushed at their
+    real size one submit later (or at capacity), published by the one small NCCL all-gather; both ranks
+    hold the same valid rows and bit-identical per-well means, whatever the push mode."""
+    torch = require_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / "x0.pt")
+    b = torch.load(tmp_path / "x1.pt")
+    assert a.keys() == b.keys() and len(a) == 6
+    for k in a:
+        assert len(a[k]["rows"]) == len(b[k]["rows"])
+        for ra, rb in zip(a[k]["rows"], b[k]["rows"]):
+            assert torch.equal(ra, rb)
+        assert torch.equal(a[k]["count"], b[k]["count"])
+        assert torch.equal(a[k]["mean"].view(torch.int64), b[k]["mean"].view(torch.int64))
+    for rep in (0, 1):                                             # and the modes agree with each other
+        for m in ("True", "False"):
+            assert torch.equal(a[("wait", rep)]["mean"].view(torch.int64), a[(m, rep)]["mean"].view(torch.int64))
+
+
+def test_plate_row_exchange_single_rank():
+    """One rank: the exchange only packs; finish() hands the blocks to the aggregator."""
+    torch = require_gpu()
+    from image_processing_suite_b200 import plate
+    rng = np.random.default_rng(3)
+    n_chunks, cf, n_max, C = 2, 4, 10, 1
+    nf = 2 + 5 * C
+    ex = plate.PlateRowExchange(n_chunks, cf, n_max, C)
+    n_obj = rng.integers(0, n_max + 1, (n_chunks, cf)).astype(np.int32)
+    ints = rng.integers(0, 400, (n_chunks, cf, n_max, 6)).astype(np.int32)
+    flts = rng.normal(5.0, 2.0, (n_chunks, cf, n_max, nf)).astype(np.float32)
+    wells = (np.arange(n_chunks * cf, dtype=np.int32) // 3).reshape(n_chunks, cf)
+    for g in range(n_chunks):
+        ex.submit(g, dev(ints[g]), dev(flts[g]), dev(n_obj[g]), dev(wells[g]), field_base=g * cf)
+    blocks = ex.finish()
+    assert ex.counts().cpu().numpy()[:, 0].tolist() == n_obj.sum(1).tolist() and ex.pushed_bytes == 0
+    agg = plate.WellAggregator(3, 8 + nf)
+    agg.add_blocks(blocks)
+    mean, count = agg.finalize()
+    assert host(count).tolist() == [int(n_obj.reshape(-1)[wells.reshape(-1) == w].sum()) for w in range(3)]
+    with pytest.raises(ValueError):
+        ex.submit(5, dev(ints[0]), dev(flts[0]), dev(n_obj[0]), dev(wells[0]))
+    ex.close()
