@@ -232,9 +232,11 @@ int ips_cosine_triu_pairs(const float* X, const int32_t* group, int n_groups, do
  * rows [N][D] float32, well [N] int32 in [0, n_wells) -> mean_out [n_wells][D] float64,
  * count_out [n_wells] int32 = rows of the well (wells without rows get NaN means, as an absent
  * group).  NaN values are skipped per column, as pandas does: every (well, column) divides by
- * its own count of non-NaN values (all-NaN -> NaN).  Any D.  Float32 rows are accumulated exactly
- * (one float64 accumulator per group of 8 binades), so the result does not depend on the order
- * in which rows, chunks or ranks arrive (up to 2^22 values per well, column and exponent class).
+ * its own count of non-NaN values (all-NaN -> NaN).  Any D.  Float32 rows are accumulated exactly:
+ * one 64-bit INTEGER sum per (well, column, group of 8 binades) in units of that group's smallest
+ * bit, added with integer atomics, so the result cannot depend on the order in which threads,
+ * chunks or ranks deliver the rows (up to 2^32 values per well, column and group); only the final
+ * float64 sum over the 32 groups rounds.  +-inf give a +-inf mean (NaN when both occur).
  */
 size_t ips_well_mean_workspace_bytes(int n_wells, int D);
 int ips_well_mean(const float* rows, const int32_t* well, double* mean_out, int32_t* count_out,
