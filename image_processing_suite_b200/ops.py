@@ -620,8 +620,10 @@ def tiff_lzw_decode(src, src_off, src_bytes, dst, dst_off, dst_bytes, to_host=Tr
         raise ValueError("strips of 4 GiB or more are not supported")
     dev = src.device
     with torch.cuda.device(dev):
-        desc64 = torch.stack([so, do]).to(dev)
-        desc32 = torch.stack([sb, db]).to(torch.uint32).to(dev)
+        # page-locked staging + asynchronous copies: a pageable .to(dev) synchronises the stream, i.e. waits
+        # for the whole batch of file bytes queued in front of it (a pipelined plate loop must not block here)
+        desc64 = torch.stack([so, do]).pin_memory().to(dev, non_blocking=True)
+        desc32 = torch.stack([sb, db]).to(torch.uint32).pin_memory().to(dev, non_blocking=True)
         status = torch.empty((n,), dtype=torch.int32, device=dev)
         capi.call("ips_tiff_lzw_decode", _ptr(src), _ptr(desc64[0]), _ptr(desc32[0]), _ptr(dst), _ptr(desc64[1]),
                   _ptr(desc32[1]), n, _ptr(status), _stream(dev))

@@ -143,7 +143,7 @@ class _InFlight:
             batch, chunks, stream, host, check, shape, keep
 
 
-def _enqueue_staged(batch, chunks, num_channels, num_planes, stream, out_ring):
+def _enqueue_staged(batch, chunks, num_channels, num_planes, stream, out_ring, trace=None):
     """Queue one staged batch of fields on ``stream`` without waiting for the device: one host->device copy
     of the (still compressed) bytes, strips decoded on the device, ONE fused z-max launch for all fields and
     channels, one device->host copy of the projections.  Raises when the batch is not uniform (the caller
@@ -153,15 +153,31 @@ def _enqueue_staged(batch, chunks, num_channels, num_planes, stream, out_ring):
     from . import batchio
     if not batch.ok():
         raise ValueError("a file of the batch could not be staged")
+    import time
     with torch.cuda.stream(stream):
+        t0 = time.perf_counter()
         src = batchio.to_device(batch)
+        if trace is not None:
+            trace.add("  queue: host->device copy", t0)
+        t0 = time.perf_counter()
         planes, check = tiffio.decode_staged(src, batch.infos, batch.bases, defer_check=True)      # [B*C*Z][H][W]
+        if trace is not None:
+            trace.add("  queue: strip tables + decode", t0)
+        t0 = time.perf_counter()
         B = len(chunks)
         H, W = planes.shape[1:]
         raw = planes.view(B, num_channels, num_planes, H, W)
         proj = ops.preprocess_fused(raw, None, bin=1, want_binned=False)["maxproj"]                # [B][C][H][W]
+        if trace is not None:
+            trace.add("  queue: projection", t0)
+        t0 = time.perf_counter()
         host = out_ring.take((B, num_channels, H, W))
+        if trace is not None:
+            trace.add("  queue: wait for a free output buffer", t0)
+        t0 = time.perf_counter()
         host.copy_(proj, non_blocking=True)
+        if trace is not None:
+            trace.add("  queue: device->host copy", t0)
     return _InFlight(batch, chunks, stream, host, check, (B, num_channels, H, W), (src, planes, proj))
 
 
@@ -262,7 +278,7 @@ def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_c
         part = batch.tag
         t0 = time.perf_counter()
         try:
-            flying.append(_enqueue_staged(batch, part, num_channels, num_planes, streams[k % 2], ring))
+            flying.append(_enqueue_staged(batch, part, num_channels, num_planes, streams[k % 2], ring, trace))
             k += 1
         except Exception as why:                      # mixed shapes, foreign formats, a missing file: field by field
             logger.info(f"batch of {len(part)} fields goes field by field ({why})")

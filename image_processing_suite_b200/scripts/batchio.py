@@ -214,7 +214,9 @@ def to_device(batch, device="cuda", stream=None):
     """ONE host->device copy of a staged batch (page-locked, asynchronous): uint8 CUDA tensor."""
     import torch
     n = max(batch.used, 16)
-    src = torch.empty((n,), dtype=torch.uint8, device=device)
+    # sizes in steps of 32 MiB: the batches of a plate differ by a few kilobytes, and a caching allocator asked
+    # for a new size each time keeps going back to cudaMalloc
+    src = torch.empty(((n + (1 << 25) - 1) >> 25 << 25,), dtype=torch.uint8, device=device)[:n]
     src.copy_(torch.from_numpy(batch.buf[:n]), non_blocking=True)
     return src
 

@@ -126,9 +126,12 @@ def parse(data):
     n_strips = -(-h // info["rows_per_strip"])
     if len(info["offsets"]) != n_strips or len(info["counts"]) != n_strips:
         raise Unsupported("strip tables do not match the image height")
-    for o, c in zip(info["offsets"], info["counts"]):
-        if o + c > len(data):
-            raise Unsupported("strip outside the file")
+    # the strip tables once more as int64 arrays: built here, on the reader thread, so that the plate loop's
+    # launching thread does not convert thousands of Python integers per batch (decode_staged)
+    info["offsets_np"] = np.asarray(info["offsets"], np.int64)
+    info["counts_np"] = np.asarray(info["counts"], np.int64)
+    if np.any(info["offsets_np"] + info["counts_np"] > len(data)):
+        raise Unsupported("strip outside the file")
     return info
 
 
@@ -155,7 +158,9 @@ def decode_staged(src, infos, bases, out=None, defer_check=False):
     so, sb, do, db = [], [], [], []
     for p, i in enumerate(infos):
         rps = i["rows_per_strip"]
-        offs, cnts = np.asarray(i["offsets"], np.int64), np.asarray(i["counts"], np.int64)
+        offs, cnts = i.get("offsets_np"), i.get("counts_np")
+        if offs is None or cnts is None:
+            offs, cnts = np.asarray(i["offsets"], np.int64), np.asarray(i["counts"], np.int64)
         rows = np.minimum(rps, h - rps * np.arange(len(offs), dtype=np.int64))
         d0, dn = p * plane + rps * w * 2 * np.arange(len(offs), dtype=np.int64), rows * w * 2
         if i["compression"] == 5:

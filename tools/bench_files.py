@@ -188,7 +188,8 @@ def main(argv=None):
             "bytes_per_field": {"maxprojection_files_in": in_bytes // a.sites, "maxprojection_files_out": C_ * H_ * W_ * 2,
                                 "feature_extraction_files_in": (C_ + 1) * H_ * W_ * 2},
             "limit": "MaxProjection moves 157 MB of file bytes per field through the host (read LZW planes, write "
-                     "uncompressed projections as the reference does): bound by the box's file I/O, not by the device",
+                     "uncompressed projections as the reference does): bound by the host side (file copies on 16 cores and "
+                     "the launching thread's share of the interpreter), not by the device",
             "outputs": "projected TIFFs byte-identical, integer features exact, float features within 1e-5 (%d sites compared)" % a.cpu_sites}
     if argv is None:
         print(json.dumps(line))
