@@ -16,6 +16,9 @@ Pinning status (see DESIGN.md "Oracle"):
     outputs (``tests/golden/*.npz``, ``tests/test_oracle_golden.py``).
   * A8 cosine: pinned against scikit-learn's ``cosine_similarity`` (the function the
     reference calls).
+  * well aggregation (``normalize.well_mean``): PINNED against the per-well table the
+    reference's own ``Normalize_CP_ami.concatenate_csv_from_s3`` writes when pycytominer's
+    ``normalize`` is stubbed to the identity (``tests/golden/well_agg.npz``).
   * A3' sum binning, A4 per-object statistics, A5 illumination estimation,
     mad_robustize: PARITY UNPINNED -- the reference holds no such arithmetic (it is
     north_star-only, or lives in CellProfiler 4.2.8 / pycytominer, neither vendored).

@@ -204,6 +204,7 @@ def main():
     cases["box_size"] = np.array(cp.BOX_SIZE)
     np.savez_compressed(os.path.join(OUT, "crops.npz"), **cases)
     tiff_golden()
+    well_agg_golden()
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)))
@@ -238,9 +239,105 @@ def tiff_golden():
     np.savez_compressed(os.path.join(OUT, "tiff_lzw.npz"), **cases)
 
 
+def well_agg_golden():
+    """The well-level aggregation of Normalize_CP_ami.concatenate_csv_from_s3 (:29-151) run by the
+    REFERENCE's own code on small tables: boto3 is an in-memory bucket, pycytominer (absent) is stubbed
+    with ``annotate`` = the plate-map merge and ``normalize`` = identity, so the CSV the reference
+    writes is its annotated per-well table -- qc_drop row removal, integer rescaling, groupby(...).agg
+    (mean | median), the outer merge of the four tables.  Stored: the input CSVs, the output CSV per
+    configuration, and the ``samples`` query the reference hands to normalize with the wells it selects."""
+    import pandas as pd
+    bucket = {}
+    seen = {}
+
+    class Body:
+        def __init__(self, b):
+            self.b = b
+
+        def read(self):
+            return self.b
+
+    class S3:
+        def get_object(self, Bucket, Key):
+            return {"Body": Body(bucket[(Bucket, Key)])}
+
+        def put_object(self, Bucket, Key, Body):
+            bucket[(Bucket, Key)] = Body.encode() if isinstance(Body, str) else Body
+
+    boto3 = types.ModuleType("boto3")
+    boto3.client = lambda *a, **k: S3()
+    botocore = types.ModuleType("botocore")
+    config = types.ModuleType("botocore.config")
+    config.Config = lambda **k: None
+    botocore.config = config
+    pyc = types.ModuleType("pycytominer")
+
+    def annotate(profiles, platemap, join_on):
+        return platemap.merge(profiles, left_on=join_on[0], right_on=join_on[1], how="inner")
+
+    def normalize(profiles, features, samples, method):
+        seen["samples"], seen["method"] = samples, method
+        seen["control_wells"] = profiles.query(samples)["Metadata_Well"].tolist()
+        return profiles.copy()
+
+    pyc.annotate, pyc.normalize = annotate, normalize
+    saved = {k: sys.modules.get(k) for k in ("boto3", "botocore", "botocore.config", "pycytominer")}
+    sys.modules.update({"boto3": boto3, "botocore": botocore, "botocore.config": config, "pycytominer": pyc})
+    try:
+        ref = _load("Normalize_CP_ami.py", "ref_normalize")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(20261019)
+    wells = [f"{r}{c:02d}" for r in "ABC" for c in range(1, 6)]
+    rows_img, tabs = [], {"Nuclei": [], "Cells": [], "Cytoplasm": []}
+    image_number = 0
+    for w in wells:
+        for site in range(1, 4 if w != "B03" else 3):          # one well has fewer sites
+            image_number += 1
+            rows_img.append({"ImageNumber": image_number, "Metadata_Well": w, "Metadata_Site": site, "Metadata_Plate": "P1",
+                             "Count_Nuclei": int(rng.integers(5, 30)), "ImageQC_Blurry": int(image_number % 7 == 0),
+                             "ExecutionTime_X": 1.5, "URL_DNA": "file:x", "Intensity_Mean": float(rng.normal(0.3, 0.05))})
+            for name in tabs:
+                for obj in range(int(rng.integers(3, 8))):
+                    tabs[name].append({"ImageNumber": image_number, "ObjectNumber": obj + 1,
+                                       "AreaShape_Area": int(rng.integers(300, 1500)),
+                                       "Intensity_MeanIntensity_DNA": float(rng.normal(0.2, 0.03)),
+                                       "Intensity_StdIntensity_DNA": float(rng.normal(0.02, 0.004)) if rng.random() > 0.1 else float("nan"),
+                                       "Location_Center_X": float(rng.uniform(0, 2160))})
+    inputs = {"Image": pd.DataFrame(rows_img).to_csv(index=False)}
+    for name, rows in tabs.items():
+        inputs[name] = pd.DataFrame(rows).to_csv(index=False)
+    pm = pd.DataFrame({"Metadata_Well": wells, "Metadata_Plate": "P1", "Metadata_ConcLevel": 1,
+                       "Metadata_Compound": ["dmso" if i % 4 == 0 else f"cmp{i}" for i in range(len(wells))]})
+    inputs["PlateMap"] = pm.to_csv(index=False)
+    for name in ("Image", "Nuclei", "Cells", "Cytoplasm"):
+        bucket[("b", f"exp/P1/24h/{name}.csv")] = inputs[name].encode()
+    bucket[("b", "exp/Plate_P1_PlateMap.csv")] = inputs["PlateMap"].encode()
+    cases = {f"in_{k}": np.frombuffer(v.encode(), np.uint8) for k, v in inputs.items()}
+    for agg in ("mean", "median"):
+        for qc_drop in (False, True):
+            ref.concatenate_csv_from_s3(bucket_name="b", plates=["P1"], times=["24h"], base_folder_path="exp",
+                                        output_bucket="out", DMSO="DMSO", output_prefix="norm", well_agg_func=agg,
+                                        no_time_subFolder=False, qc_drop=qc_drop)
+            key = f"{agg}_{'qc' if qc_drop else 'all'}"
+            cases[f"out_{key}"] = np.frombuffer(bucket[("out", "norm/P1/Normalized_features_24h.csv")], np.uint8)
+            cases[f"controls_{key}"] = np.array(seen["control_wells"])
+    cases["samples_query"] = np.array(seen["samples"])
+    cases["method"] = np.array(seen["method"])
+    cases["pandas_version"] = np.array(pd.__version__)
+    np.savez_compressed(os.path.join(OUT, "well_agg.npz"), **cases)
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["tiff"]:
         os.makedirs(OUT, exist_ok=True)
         tiff_golden()
+    elif sys.argv[1:] == ["wellagg"]:
+        os.makedirs(OUT, exist_ok=True)
+        well_agg_golden()
     else:
         main()

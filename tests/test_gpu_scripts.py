@@ -234,6 +234,43 @@ def test_normalize_script_matches_pandas_and_oracle(tmp_path, monkeypatch, qc_dr
         nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", "sum", False, qc_drop, s3)
 
 
+@pytest.mark.parametrize("agg", ["mean", "median"])
+@pytest.mark.parametrize("qc_drop", [False, True])
+def test_normalize_aggregation_matches_reference_golden(tmp_path, monkeypatch, golden_dir, agg, qc_drop):
+    """tests/golden/well_agg.npz holds the per-well table the REFERENCE's concatenate_csv_from_s3 writes
+    when pycytominer's normalize is the identity (oracle/make_golden.py): the drop-in's table plumbing and
+    GPU aggregation (ips_well_mean_f64 / ips_well_median_f64) must reproduce it column by column, and hand
+    the same control wells to the normalisation."""
+    require_gpu()
+    from image_processing_suite_b200.scripts import Normalize_CP_ami as nz, storage
+    g = np.load(os.path.join(golden_dir, "well_agg.npz"))
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    s3 = storage.client()
+    for name in ("Image", "Nuclei", "Cells", "Cytoplasm"):
+        s3.put_object(Bucket="b", Key=f"exp/P1/24h/{name}.csv", Body=g[f"in_{name}"].tobytes())
+    s3.put_object(Bucket="b", Key="exp/Plate_P1_PlateMap.csv", Body=g["in_PlateMap"].tobytes())
+    seen = {}
+
+    def identity(profiles, features, control_mask):
+        seen["controls"] = profiles.loc[np.asarray(control_mask, bool), "Metadata_Well"].tolist()
+        meta = profiles[[c for c in profiles.columns if c not in features]].reset_index(drop=True)
+        return pd.concat([meta, profiles[features].reset_index(drop=True)], axis=1)
+
+    monkeypatch.setattr(nz, "normalize_mad_robustize", identity)
+    keys = nz.concatenate_csv_from_s3("b", ["P1"], ["24h"], "exp", "out", "DMSO", "norm", agg, False, qc_drop, s3)
+    got = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key=keys[0])["Body"].read()))
+    key = f"{agg}_{'qc' if qc_drop else 'all'}"
+    ref = pd.read_csv(io.BytesIO(g[f"out_{key}"].tobytes()))
+    assert sorted(got.columns) == sorted(ref.columns)
+    assert list(got["Metadata_Well"]) == list(ref["Metadata_Well"])
+    for c in ref.columns:
+        if c.startswith("Metadata"):
+            assert list(got[c]) == list(ref[c]), c
+        else:
+            np.testing.assert_allclose(got[c].to_numpy(float), ref[c].to_numpy(float), rtol=1e-12, err_msg=c)
+    assert seen["controls"] == g[f"controls_{key}"].tolist()
+
+
 def test_feature_select_cosine_script(tmp_path, monkeypatch):
     """The cosine drop-in with an identity feature selection: double sigmoid and per-group mean
     cosine (all groups in one kernel call) against scikit-learn, group by group."""

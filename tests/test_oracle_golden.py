@@ -104,3 +104,25 @@ def test_scale_to_8bit_matches_reference(golden_dir, case):
     out = crops.scale_to_8bit(g[f"{case}_in"])
     assert out.dtype == np.uint8
     np.testing.assert_array_equal(out, g[f"{case}_out"])
+
+
+def test_well_mean_matches_reference_aggregation(golden_dir):
+    """tests/golden/well_agg.npz: the per-well table written by the reference's own
+    Normalize_CP_ami.concatenate_csv_from_s3 (pycytominer stubbed out, oracle/make_golden.py).  The
+    oracle's well_mean on the object tables reproduces its columns (mean, all images kept), NaN cells
+    skipped per column as pandas does."""
+    import io
+    import pandas as pd
+    from oracle import normalize as o_norm
+    g = np.load(os.path.join(golden_dir, "well_agg.npz"))
+    out = pd.read_csv(io.BytesIO(g["out_mean_all"].tobytes()))
+    image = pd.read_csv(io.BytesIO(g["in_Image"].tobytes()))
+    for name, prefix in (("Nuclei", "DNA_"), ("Cells", "Cell_"), ("Cytoplasm", "Cyto_")):
+        tab = pd.read_csv(io.BytesIO(g[f"in_{name}"].tobytes())).merge(image[["ImageNumber", "Metadata_Well"]], on="ImageNumber")
+        feats = [c for c in tab.columns if c not in ("ImageNumber", "Metadata_Well")]
+        assert tab[feats].isna().to_numpy().any()                # the fixture does exercise NaN skipping
+        wells, means = o_norm.well_mean(tab[feats].to_numpy(float), tab["Metadata_Well"].to_numpy())
+        ref = out.set_index("Metadata_Well").loc[wells, [prefix + f for f in feats]].to_numpy(float)
+        np.testing.assert_allclose(means, ref, rtol=1e-12)
+    assert str(g["method"]) == "mad_robustize"
+    assert str(g["samples_query"]) == "Metadata_Compound == 'DMSO' and Metadata_Timepoint == '24h'"
