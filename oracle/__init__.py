@@ -15,7 +15,8 @@ Pinning status (see DESIGN.md "Oracle"):
     stubbed) and the real Pillow, and the restatements here are checked against those
     outputs (``tests/golden/*.npz``, ``tests/test_oracle_golden.py``).
   * A8 cosine: pinned against scikit-learn's ``cosine_similarity`` (the function the
-    reference calls).
+    reference calls), and with the double sigmoid against the files the reference's own
+    ``Feature_select_cosine_ami`` loop writes (``tests/golden/cosine_script.npz``).
   * well aggregation (``normalize.well_mean``): PINNED against the per-well table the
     reference's own ``Normalize_CP_ami.concatenate_csv_from_s3`` writes when pycytominer's
     ``normalize`` is stubbed to the identity (``tests/golden/well_agg.npz``).

@@ -205,6 +205,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "crops.npz"), **cases)
     tiff_golden()
     well_agg_golden()
+    cosine_script_golden()
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)))
@@ -332,8 +333,88 @@ def well_agg_golden():
     np.savez_compressed(os.path.join(OUT, "well_agg.npz"), **cases)
 
 
+def cosine_script_golden():
+    """Feature_select_cosine_ami.concatenate_normalized_csv_from_s3 (:39-164) run by the REFERENCE's own
+    code: boto3 is an in-memory bucket, pycytominer.feature_select (absent) is stubbed with the identity
+    selection (it writes the profiles it was given), so the files the reference writes pin its double
+    sigmoid (:26-27, :117-118), the fillna / grouping rules and the per-group mean cosine (:131-156)."""
+    import pandas as pd
+    bucket = {}
+
+    class Body:
+        def __init__(self, b):
+            self.b = b
+
+        def read(self):
+            return self.b
+
+    class S3:
+        def get_object(self, Bucket, Key):
+            return {"Body": Body(bucket[(Bucket, Key)])}
+
+        def put_object(self, Bucket, Key, Body):
+            bucket[(Bucket, Key)] = Body.encode() if isinstance(Body, str) else Body
+
+        def list_objects_v2(self, Bucket, Prefix, Delimiter=None):
+            keys = sorted(k for b, k in bucket if b == Bucket and k.startswith(Prefix)
+                          and (Delimiter is None or Delimiter not in k[len(Prefix):]))
+            return {"Contents": [{"Key": k} for k in keys]}
+
+    boto3 = types.ModuleType("boto3")
+    boto3.client = lambda *a, **k: S3()
+    pyc = types.ModuleType("pycytominer")
+
+    def feature_select(profiles, features, samples, operation, output_file, output_type, na_cutoff=None, corr_threshold=None):
+        profiles.to_csv(output_file, index=False)
+
+    pyc.feature_select = feature_select
+    saved = {k: sys.modules.get(k) for k in ("boto3", "pycytominer")}
+    sys.modules.update({"boto3": boto3, "pycytominer": pyc})
+    try:
+        ref = _load("Feature_select_cosine_ami.py", "ref_cosine_script")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(20261020)
+    cases = {}
+    for plate in ("P1", "P2"):
+        for tp in ("24h", "48h"):
+            frame = []
+            for comp, reps in (("DMSO", 5), ("CMP1", 4), ("CMP2", 1), ("CMP3", 3)):
+                for r in range(reps):
+                    d = {"Metadata_Compound": comp, "Metadata_ConcLevel": 1 + (r % 2 if comp == "CMP1" else 0),
+                         "Metadata_Well": f"{comp}{r}", "Metadata_Plate": plate, "Metadata_Timepoint": tp}
+                    # short cells: csv.Sniffer (read_csv_from_s3, :33-36) must see several rows in 1024 characters
+                    d.update({f"f{j}": round(float(rng.normal(0, 3)), 3) for j in range(12)})
+                    frame.append(d)
+            df = pd.DataFrame(frame)
+            df.loc[2, "f3"] = np.nan
+            df.loc[7, "f0"] = 0.0
+            text = df.to_csv(index=False)
+            bucket[("b", f"exp/{plate}/Normalized_features_{tp}.csv")] = text.encode()
+            cases[f"in_{plate}_{tp}"] = np.frombuffer(text.encode(), np.uint8)
+    bucket[("b", "exp/P1/sub/Normalized_features_x.csv")] = b"deeper than the plate folder: not listed"
+    import tempfile
+    for per_time in (False, True):
+        with tempfile.TemporaryDirectory() as tmp:
+            ref.concatenate_normalized_csv_from_s3(bucket_name="b", plates=["P1", "P2"], base_folder_path="exp",
+                                                   per_time=per_time, output_bucket="out", output_prefix="res", exp="EXP",
+                                                   na_cutoff=0.5, corr_3hold=0.9, local_dir=tmp)
+        tag = "pertime" if per_time else "global"
+        for name in ("EXP_CP_features_selected_allTimes_raw.csv", "EXP_CP_features_selected_allTimes_dSig.csv",
+                     "EXP_Average_cosine_similarity.csv"):
+            cases[f"{tag}_{name}"] = np.frombuffer(bucket[("out", f"res/{name}")], np.uint8)
+    np.savez_compressed(os.path.join(OUT, "cosine_script.npz"), **cases)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["tiff"]:
+    if sys.argv[1:] == ["cosine_script"]:
+        os.makedirs(OUT, exist_ok=True)
+        cosine_script_golden()
+    elif sys.argv[1:] == ["tiff"]:
         os.makedirs(OUT, exist_ok=True)
         tiff_golden()
     elif sys.argv[1:] == ["wellagg"]:

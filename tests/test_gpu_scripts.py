@@ -318,6 +318,47 @@ def test_feature_select_cosine_script(tmp_path, monkeypatch):
     assert len(saved) == len(sims)
 
 
+@pytest.mark.parametrize("per_time", [False, True])
+def test_feature_select_cosine_script_matches_reference_golden(tmp_path, monkeypatch, golden_dir, per_time):
+    """tests/golden/cosine_script.npz: the files the REFERENCE's concatenate_normalized_csv_from_s3 writes
+    with an identity feature selection (oracle/make_golden.py).  The drop-in (ips_double_sigmoid_abs, all
+    groups in one ips_cosine_triu call) writes the same tables: keys, order, values."""
+    require_gpu()
+    from image_processing_suite_b200.scripts import Feature_select_cosine_ami as fs, storage
+    g = np.load(os.path.join(golden_dir, "cosine_script.npz"))
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    s3 = storage.client()
+    for plate in ("P1", "P2"):
+        for tp in ("24h", "48h"):
+            s3.put_object(Bucket="b", Key=f"exp/{plate}/Normalized_features_{tp}.csv", Body=g[f"in_{plate}_{tp}"].tobytes())
+    s3.put_object(Bucket="b", Key="exp/P1/sub/Normalized_features_x.csv", Body=b"deeper than the plate folder: not listed")
+    ident = lambda profiles, features, **kw: profiles
+    fs.concatenate_normalized_csv_from_s3("b", ["P1", "P2"], "exp", per_time, "out", "res", "EXP", 0.5, 0.9,
+                                          feature_select=ident, s3=s3)
+    tag = "pertime" if per_time else "global"
+
+    def both(name):
+        got = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key=f"res/{name}")["Body"].read()))
+        return got, pd.read_csv(io.BytesIO(g[f"{tag}_{name}"].tobytes()))
+
+    for name, tol in (("EXP_CP_features_selected_allTimes_raw.csv", 0.0), ("EXP_CP_features_selected_allTimes_dSig.csv", 1e-12)):
+        got, ref = both(name)
+        assert list(got.columns) == list(ref.columns) and len(got) == len(ref)
+        for c in ref.columns:
+            if "Metadata" in c:
+                assert list(got[c]) == list(ref[c]), c
+            else:
+                # pandas writes small floats with 15 decimals: the files hold the values to 1e-15 absolute
+                np.testing.assert_allclose(got[c].to_numpy(float), ref[c].to_numpy(float), rtol=tol, atol=2e-15 if tol else 0.0,
+                                           equal_nan=True, err_msg=c)
+    got, ref = both("EXP_Average_cosine_similarity.csv")
+    assert list(got.columns) == list(ref.columns)
+    for c in fs.GROUP_KEYS:
+        assert list(got[c]) == list(ref[c]), c
+    np.testing.assert_allclose(got["average_cosine_similarity"].to_numpy(float), ref["average_cosine_similarity"].to_numpy(float),
+                               atol=1e-5, equal_nan=True)
+
+
 def test_pycyto_pertime_script(tmp_path, monkeypatch):
     """Pycyto_pertime drop-in with an identity feature selection against pandas / oracle /
     scikit-learn on the same tables (per-pair similarity vectors included)."""

@@ -126,3 +126,27 @@ def test_well_mean_matches_reference_aggregation(golden_dir):
         np.testing.assert_allclose(means, ref, rtol=1e-12)
     assert str(g["method"]) == "mad_robustize"
     assert str(g["samples_query"]) == "Metadata_Compound == 'DMSO' and Metadata_Timepoint == '24h'"
+
+
+@pytest.mark.parametrize("tag", ["global", "pertime"])
+def test_double_sigmoid_and_group_cosine_match_reference_script(golden_dir, tag):
+    """tests/golden/cosine_script.npz: the files written by the reference's own
+    Feature_select_cosine_ami.concatenate_normalized_csv_from_s3 with an identity feature selection
+    (oracle/make_golden.py).  The oracle's double sigmoid and per-group mean cosine reproduce them."""
+    import io
+    import pandas as pd
+    from oracle import normalize as o_norm
+    g = np.load(os.path.join(golden_dir, "cosine_script.npz"))
+    raw = pd.read_csv(io.BytesIO(g[f"{tag}_EXP_CP_features_selected_allTimes_raw.csv"].tobytes()))
+    dsig = pd.read_csv(io.BytesIO(g[f"{tag}_EXP_CP_features_selected_allTimes_dSig.csv"].tobytes()))
+    avg = pd.read_csv(io.BytesIO(g[f"{tag}_EXP_Average_cosine_similarity.csv"].tobytes()))
+    feats = [c for c in raw.columns if "Metadata" not in c]
+    # pandas writes small floats with 15 decimals: the file holds the values to 1e-15 absolute
+    np.testing.assert_allclose(np.abs(o_norm.double_sigmoid(raw[feats].to_numpy(float))), dsig[feats].to_numpy(float),
+                               rtol=1e-13, atol=2e-15, equal_nan=True)
+    keys = ["Metadata_Compound", "Metadata_Timepoint", "Metadata_ConcLevel"]
+    assert len(avg) == len(dsig[keys].drop_duplicates())
+    for _, row in avg.iterrows():
+        grp = dsig[(dsig[keys[0]] == row[keys[0]]) & (dsig[keys[1]] == row[keys[1]]) & (dsig[keys[2]] == row[keys[2]])]
+        want = cosine.triu_mean(grp[feats].fillna(0).to_numpy(float))
+        np.testing.assert_allclose(want, row["average_cosine_similarity"], rtol=1e-12, equal_nan=True)
