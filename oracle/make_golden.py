@@ -206,6 +206,7 @@ def main():
     tiff_golden()
     well_agg_golden()
     cosine_script_golden()
+    pycyto_golden()
     print("golden fixtures written to", os.path.normpath(OUT))
     for f in sorted(os.listdir(OUT)):
         print(" ", f, os.path.getsize(os.path.join(OUT, f)))
@@ -410,8 +411,84 @@ def cosine_script_golden():
     np.savez_compressed(os.path.join(OUT, "cosine_script.npz"), **cases)
 
 
+def pycyto_golden():
+    """Pycyto_pertime.concatenate_csv_from_s3 (:29-172) run by the REFERENCE's own code: boto3 is an
+    in-memory bucket, pycytominer's normalize and feature_select are the identity, so the three files it
+    writes pin the four-key groupby means (:69-72), the merge order, |double sigmoid| (:92-93) and the
+    per-group cosine values and means (:115-163).  (The Image table carries no free-text column: the
+    reference's ``dtype == 'object'`` test (:65) does not catch ``str`` columns under current pandas.)"""
+    import pandas as pd
+    bucket = {}
+
+    class Body:
+        def __init__(self, b):
+            self.b = b
+
+        def read(self):
+            return self.b
+
+    class S3:
+        def get_object(self, Bucket, Key):
+            return {"Body": Body(bucket[(Bucket, Key)])}
+
+        def put_object(self, Bucket, Key, Body):
+            bucket[(Bucket, Key)] = Body.encode() if isinstance(Body, str) else Body
+
+    boto3 = types.ModuleType("boto3")
+    boto3.client = lambda *a, **k: S3()
+    pyc = types.ModuleType("pycytominer")
+    pyc.annotate = lambda *a, **k: None
+    pyc.normalize = lambda profiles, features, samples, method: profiles.copy()
+
+    def feature_select(profiles, features, samples, operation, output_file, output_type):
+        profiles.to_csv(output_file, index=False)
+
+    pyc.feature_select = feature_select
+    saved = {k: sys.modules.get(k) for k in ("boto3", "pycytominer")}
+    sys.modules.update({"boto3": boto3, "pycytominer": pyc})
+    try:
+        ref = _load("Pycyto_pertime.py", "ref_pycyto")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rng = np.random.default_rng(20261021)
+    img_rows, tabs = [], {"Nuclei": [], "Cells": [], "Cytoplasm": []}
+    n = 0
+    for wi in range(12):
+        comp = "DMSO" if wi % 3 == 0 else f"CMP{wi % 4}"
+        for site in (1, 2):
+            n += 1
+            img_rows.append({"ImageNumber": n, "Metadata_Plate": "Plate_1", "Metadata_Site": site, "Metadata_Well": f"W{wi:02d}",
+                             "Metadata_Timepoint": "24h", "Metadata_Compound": comp, "Metadata_ConcLevel": 1 + wi % 2,
+                             "Count_Nuclei": int(rng.integers(10, 40)), "Granularity_1": round(float(rng.normal(5, 1)), 4)})
+            for name in tabs:
+                for _ in range(int(rng.integers(3, 6))):
+                    tabs[name].append({"ImageNumber": n, "AreaShape_Area": int(rng.integers(300, 900)),
+                                       "Intensity_Mean_DNA": round(float(rng.normal(0.2, 0.05)), 5),
+                                       "Texture_1": round(float(rng.normal(1, 0.3)), 4)})
+    cases = {}
+    for name, rows in [("Image", img_rows)] + list(tabs.items()):
+        text = pd.DataFrame(rows).to_csv(index=False)
+        bucket[("b", f"proj/Plate_1/24h/{name}.csv")] = text.encode()
+        cases[f"in_{name}"] = np.frombuffer(text.encode(), np.uint8)
+    import contextlib
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()):
+        ref.concatenate_csv_from_s3(bucket_name="b", times=["24h"], base_folder_path="proj/Plate_1", output_bucket="out",
+                                    output_prefix="res", local_dir=tmp)
+    for name in ("CP_features_selected.csv", "CPfeatures_average_cosine_similarity.csv", "CPfeatures_cosine_similarities.csv"):
+        cases[name] = np.frombuffer(bucket[("out", f"res/24h/{name}")], np.uint8)
+    np.savez_compressed(os.path.join(OUT, "pycyto_pertime.npz"), **cases)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["cosine_script"]:
+    if sys.argv[1:] == ["pycyto"]:
+        os.makedirs(OUT, exist_ok=True)
+        pycyto_golden()
+    elif sys.argv[1:] == ["cosine_script"]:
         os.makedirs(OUT, exist_ok=True)
         cosine_script_golden()
     elif sys.argv[1:] == ["tiff"]:

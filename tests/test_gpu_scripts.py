@@ -420,3 +420,49 @@ def test_pycyto_pertime_script(tmp_path, monkeypatch):
             assert np.isnan(averaged.loc[k, "average_cosine_similarity"])
         k += 1
     assert k == len(averaged)
+
+
+def test_pycyto_pertime_script_matches_reference_golden(tmp_path, monkeypatch, golden_dir):
+    """tests/golden/pycyto_pertime.npz: the three files the REFERENCE's Pycyto_pertime.concatenate_csv_from_s3
+    writes when pycytominer's normalize and feature_select are the identity (oracle/make_golden.py).  The
+    drop-in's four-key group means (ips_well_mean_f64), |double sigmoid| and per-pair cosine values
+    (ips_cosine_triu_pairs) reproduce them, suffixes of the colliding column names included."""
+    require_gpu()
+    from image_processing_suite_b200.scripts import Pycyto_pertime as pp, storage
+    g = np.load(os.path.join(golden_dir, "pycyto_pertime.npz"))
+    monkeypatch.setenv("IPS_STORAGE_ROOT", str(tmp_path))
+    s3 = storage.client()
+    for name in ("Image", "Nuclei", "Cells", "Cytoplasm"):
+        s3.put_object(Bucket="b", Key=f"proj/Plate_1/24h/{name}.csv", Body=g[f"in_{name}"].tobytes())
+
+    def identity(profiles, features, control_mask):
+        meta = profiles[[c for c in profiles.columns if c not in features]].reset_index(drop=True)
+        return pd.concat([meta, profiles[features].reset_index(drop=True)], axis=1)
+
+    monkeypatch.setattr(pp, "normalize_mad_robustize", identity)
+    ident = lambda profiles, features, **kw: profiles
+    pp.concatenate_csv_from_s3("b", ["24h"], "proj/Plate_1", "out", "res", feature_select=ident, s3=s3)
+
+    def both(name):
+        got = pd.read_csv(io.BytesIO(s3.get_object(Bucket="out", Key=f"res/24h/{name}")["Body"].read()))
+        return got, pd.read_csv(io.BytesIO(g[name].tobytes()))
+
+    got, ref = both("CP_features_selected.csv")
+    assert sorted(got.columns) == sorted(ref.columns) and len(got) == len(ref)
+    assert [c for c in got.columns if "Metadata" not in c] == [c for c in ref.columns if "Metadata" not in c]
+    for c in ref.columns:
+        if c in pp.KEYS:
+            assert list(got[c]) == list(ref[c]), c
+        else:
+            np.testing.assert_allclose(got[c].to_numpy(float), ref[c].to_numpy(float), rtol=1e-12, atol=2e-15, err_msg=c)
+    got, ref = both("CPfeatures_average_cosine_similarity.csv")
+    assert list(got.columns) == list(ref.columns)
+    for c in ("Metadata_compound_code", "Metadata_Timepoint", "Metadata_compound_concentration"):
+        assert list(got[c]) == list(ref[c]), c
+    np.testing.assert_allclose(got["average_cosine_similarity"].to_numpy(float), ref["average_cosine_similarity"].to_numpy(float),
+                               atol=1e-5, equal_nan=True)
+    got, ref = both("CPfeatures_cosine_similarities.csv")
+    assert list(got.columns) == list(ref.columns) and len(got) == len(ref)
+    for a, b in zip(got["cosine_similarities"], ref["cosine_similarities"]):
+        va, vb = (np.array(x.strip("[]").split(), dtype=float) for x in (a, b))
+        np.testing.assert_allclose(va, vb, atol=1e-5)
