@@ -81,16 +81,18 @@ __device__ __forceinline__ void wm_flush(const WmPlain& t, const WmOut& o, int w
   if (d == 0) atomicAdd(&o.rowcnt[w], t.k);
 }
 
-// One value of the thread's column.  Hot path: a float32 of one of the two classes the thread holds,
-// widened and added.  Everything else (zero, NaN, inf, the top class, a third class) takes the branch.
+// One value of the thread's column.  Hot path, branch-free (the lanes of a warp are different columns
+// in different classes: an if-chain would run every arm for every warp): the value, widened, is added
+// to the slot whose class it has, zero to the other.  Everything else (zero, NaN, inf, the top class, a
+// third class) takes the one rare branch.
 __device__ __forceinline__ void wm_take(WmExact& t, float v, const WmOut& o, int w, int D, int d) {
-  ++t.k;
   const uint32_t bits = __float_as_uint(v);
   const int c = (int)((bits >> 26) & 31u);
   const double x = (double)v;
-  if (c == t.c0) t.a0 += x;
-  else if (c == t.c1) t.a1 += x;
-  else {
+  const bool h0 = c == t.c0, h1 = c == t.c1;
+  t.a0 += h0 ? x : 0.0;
+  t.a1 += h1 ? x : 0.0;
+  if (!(h0 || h1)) {
     const uint32_t absb = bits & 0x7fffffffu;
     if (absb == 0u) return;                                   // +-0
     if (absb >= 0x7f800000u) {                                // NaN: skipped, not counted; inf: flagged
@@ -108,7 +110,6 @@ __device__ __forceinline__ void wm_take(WmExact& t, float v, const WmOut& o, int
   }
 }
 __device__ __forceinline__ void wm_take(WmPlain& t, double v, const WmOut&, int, int, int) {
-  ++t.k;
   if (v == v) t.acc += v;
   else ++t.nan;
 }
@@ -127,6 +128,7 @@ __device__ __forceinline__ void wm_thread_rows(const T* __restrict__ pv, const i
       cur = w;
       run = Run();
     }
+    if (!UNIFORM) ++run.k;                                  // rows of the well (UNIFORM: all of them, set below)
     wm_take(run, v, out, cur, D, d);
   };
   // batches of WM_UNROLL rows, the next batch's loads issued before the current one is summed
@@ -149,6 +151,7 @@ __device__ __forceinline__ void wm_thread_rows(const T* __restrict__ pv, const i
     for (int j = 0; j < WM_UNROLL; ++j) take(v[j], UNIFORM ? w0 : s_well[(b * WM_UNROLL + j) * subs]);
   }
   for (int i = full * WM_UNROLL; i < mine; ++i, p += stride) take(*p, UNIFORM ? w0 : s_well[i * subs]);
+  if (UNIFORM) run.k = mine;
   if (cur >= 0) wm_flush(run, out, cur, D, d);
 }
 

@@ -225,7 +225,7 @@ class _PinnedRing:
 
 
 def run(bucket_data_set, data_set, num_channels, num_planes, bucket_images, s3_client=None, batch_fields=4,
-        threads=12):
+        threads=8):
     """The CLI loop of MaxProjection.py:64-95 at plate scale: the chunks (one field each) are staged
     ``batch_fields`` at a time by reader threads (scripts/batchio.py), projected with one launch per
     batch, and written by writer threads while the next batch is being read."""

@@ -125,7 +125,7 @@ def main(argv=None):
     ap.add_argument("--batch", type=int, default=8, help="sites per Feature_extraction batch")
     ap.add_argument("--mp-batch", type=int, default=4, help="fields per MaxProjection batch")
     ap.add_argument("--threads", type=int, default=8, help="reader threads of Feature_extraction")
-    ap.add_argument("--mp-threads", type=int, default=16, help="reader / writer threads of MaxProjection")
+    ap.add_argument("--mp-threads", type=int, default=8, help="reader / writer threads of MaxProjection")
     ap.add_argument("--keep", action="store_true")
     a = ap.parse_args(argv)
     import pandas as pd
