@@ -45,32 +45,30 @@ struct WmOut {
   int* flags;        // [n_wells][D] bit 0: +inf seen, bit 1: -inf seen (exact path only)
 };
 
-// What a thread carries for the well it is in.  Exact path: the sums of the two exponent classes
-// seen last (a column's values rarely straddle more) as float64 -- at most 64 values of one class,
-// i.e. integers below 2^37 in units of the class: exact -- turned into the integer multiple of the
-// class unit when they leave; rows taken, NaNs skipped, inf flags.
+// What a thread carries for the well it is in: the exact path's class slots (wellmean_exact.cuh) or
+// one float64 sum, the rows taken and the NaNs skipped.
 struct WmExact {
-  double a0 = 0.0, a1 = 0.0;
-  int c0 = -1, c1 = -1, k = 0, nan = 0, inf = 0;
+  WmxSlots s;
+  int k = 0;
 };
 struct WmPlain {
   double acc = 0.0;
   int k = 0, nan = 0;
 };
 
-__device__ __forceinline__ unsigned long long* wm_class_sums(const WmOut& o, int w, int D, int d) {
-  return reinterpret_cast<unsigned long long*>(o.sums) + ((size_t)w * D + d) * WM_CLASSES;
+// where a class sum goes when it leaves a thread: one 64-bit integer atomic
+struct WmSink {
+  unsigned long long* sums;      // the 32 class sums of (well, column)
+  __device__ __forceinline__ void operator()(int c, unsigned long long units) const { atomicAdd(sums + c, units); }
+};
+__device__ __forceinline__ WmSink wm_sink(const WmOut& o, int w, int D, int d) {
+  return WmSink{reinterpret_cast<unsigned long long*>(o.sums) + ((size_t)w * D + d) * WM_CLASSES};
 }
-// a class sum held as float64 -> its (exact) integer multiple of the class unit
-__device__ __forceinline__ unsigned long long wm_units(double a, int c) {
-  return (unsigned long long)__double2ll_rn(a * wmx_pow2(-wmx_unit_exp(c)));
-}
+
 __device__ __forceinline__ void wm_flush(const WmExact& t, const WmOut& o, int w, int D, int d) {
-  unsigned long long* s = wm_class_sums(o, w, D, d);
-  if (t.c0 >= 0 && t.a0 != 0.0) atomicAdd(s + t.c0, wm_units(t.a0, t.c0));
-  if (t.c1 >= 0 && t.a1 != 0.0) atomicAdd(s + t.c1, wm_units(t.a1, t.c1));
-  if (t.k > t.nan) atomicAdd(&o.colcnt[(size_t)w * D + d], t.k - t.nan);
-  if (t.inf) atomicOr(&o.flags[(size_t)w * D + d], t.inf);
+  wmx_leave(t.s, wm_sink(o, w, D, d));
+  if (t.k > t.s.nan) atomicAdd(&o.colcnt[(size_t)w * D + d], t.k - t.s.nan);
+  if (t.s.inf) atomicOr(&o.flags[(size_t)w * D + d], t.s.inf);
   if (d == 0) atomicAdd(&o.rowcnt[w], t.k);
 }
 __device__ __forceinline__ void wm_flush(const WmPlain& t, const WmOut& o, int w, int D, int d) {
@@ -81,33 +79,33 @@ __device__ __forceinline__ void wm_flush(const WmPlain& t, const WmOut& o, int w
   if (d == 0) atomicAdd(&o.rowcnt[w], t.k);
 }
 
-// One value of the thread's column.  Hot path, branch-free (the lanes of a warp are different columns
-// in different classes: an if-chain would run every arm for every warp): the value, widened, is added
-// to the slot whose class it has, zero to the other.  Everything else (zero, NaN, inf, the top class, a
-// third class) takes the one rare branch.
-__device__ __forceinline__ void wm_take(WmExact& t, float v, const WmOut& o, int w, int D, int d) {
-  const uint32_t bits = __float_as_uint(v);
-  const int c = (int)((bits >> 26) & 31u);
-  const double x = (double)v;
-  const bool h0 = c == t.c0, h1 = c == t.c1;
-  t.a0 += h0 ? x : 0.0;
-  t.a1 += h1 ? x : 0.0;
-  if (!(h0 || h1)) {
-    const uint32_t absb = bits & 0x7fffffffu;
-    if (absb == 0u) return;                                   // +-0
-    if (absb >= 0x7f800000u) {                                // NaN: skipped, not counted; inf: flagged
-      if (absb > 0x7f800000u) ++t.nan;
-      else t.inf |= (bits >> 31) ? 2 : 1;
-      return;
-    }
-    if (c == WM_CLASSES - 1) {                                // never held in a slot: NaN and inf would match it
-      atomicAdd(wm_class_sums(o, w, D, d) + c, wm_units(x, c));
-      return;
-    }
-    if (t.c1 >= 0 && t.a1 != 0.0) atomicAdd(wm_class_sums(o, w, D, d) + t.c1, wm_units(t.a1, t.c1));
-    t.c1 = t.c0; t.a1 = t.a0;                                 // a third class: the older one leaves
-    t.c0 = c; t.a0 = x;
+// One batch of WM_UNROLL values of the thread's column, all of well w.  Exact path: the branch-free
+// adds for all of them first, then ONE test for the batch; values no slot took (zero, NaN, inf, a new
+// class) are seen again by wmx_slow -- class sums do not depend on the order, so deferring them is free,
+// and the hot loop has no control flow (an if per value cost eleven register moves per value at the
+// merge points).
+__device__ __forceinline__ void wm_batch(WmExact& t, const float (&v)[WM_UNROLL], const WmOut& o, int w, int D, int d) {
+  unsigned odd = 0u;
+#pragma unroll
+  for (int j = 0; j < WM_UNROLL; ++j)
+    odd |= wmx_fast(t.s, __float_as_uint(v[j]), (double)v[j]) ? (1u << j) : 0u;
+  if (odd) {
+    const WmSink sink = wm_sink(o, w, D, d);
+#pragma unroll
+    for (int j = 0; j < WM_UNROLL; ++j)
+      if (odd & (1u << j)) wmx_slow(t.s, __float_as_uint(v[j]), (double)v[j], sink);
   }
+}
+__device__ __forceinline__ void wm_batch(WmPlain& t, const double (&v)[WM_UNROLL], const WmOut&, int, int, int) {
+#pragma unroll
+  for (int j = 0; j < WM_UNROLL; ++j) {
+    if (v[j] == v[j]) t.acc += v[j];
+    else ++t.nan;
+  }
+}
+// one value (tails of a thread's rows, tiles that span wells)
+__device__ __forceinline__ void wm_take(WmExact& t, float v, const WmOut& o, int w, int D, int d) {
+  if (wmx_fast(t.s, __float_as_uint(v), (double)v)) wmx_slow(t.s, __float_as_uint(v), (double)v, wm_sink(o, w, D, d));
 }
 __device__ __forceinline__ void wm_take(WmPlain& t, double v, const WmOut&, int, int, int) {
   if (v == v) t.acc += v;
@@ -121,14 +119,14 @@ __device__ __forceinline__ void wm_thread_rows(const T* __restrict__ pv, const i
                                                int subs, int w0, const WmOut& out, int D, int d, int n_wells) {
   Run run;
   int cur = UNIFORM ? w0 : -2;                              // -2: no well yet
-  auto take = [&](T v, int w) {
+  auto take = [&](T v, int w) {                             // one row, whatever its well
     if (!UNIFORM && w != cur) {
       if (w < 0 || w >= n_wells) return;                    // rows without a well (id out of range) are dropped
       if (cur >= 0) wm_flush(run, out, cur, D, d);
       cur = w;
       run = Run();
     }
-    if (!UNIFORM) ++run.k;                                  // rows of the well (UNIFORM: all of them, set below)
+    ++run.k;
     wm_take(run, v, out, cur, D, d);
   };
   // batches of WM_UNROLL rows, the next batch's loads issued before the current one is summed
@@ -147,11 +145,15 @@ __device__ __forceinline__ void wm_thread_rows(const T* __restrict__ pv, const i
 #pragma unroll
       for (int j = 0; j < WM_UNROLL; ++j, p += stride) nx[j] = *p;
     }
+    if (UNIFORM) {
+      run.k += WM_UNROLL;
+      wm_batch(run, v, out, cur, D, d);
+    } else {
 #pragma unroll
-    for (int j = 0; j < WM_UNROLL; ++j) take(v[j], UNIFORM ? w0 : s_well[(b * WM_UNROLL + j) * subs]);
+      for (int j = 0; j < WM_UNROLL; ++j) take(v[j], s_well[(b * WM_UNROLL + j) * subs]);
+    }
   }
   for (int i = full * WM_UNROLL; i < mine; ++i, p += stride) take(*p, UNIFORM ? w0 : s_well[i * subs]);
-  if (UNIFORM) run.k = mine;
   if (cur >= 0) wm_flush(run, out, cur, D, d);
 }
 

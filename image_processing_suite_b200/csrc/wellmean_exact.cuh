@@ -49,3 +49,57 @@ WMX_HD double wmx_total(const long long* acc) {
     if (acc[c]) s += (double)acc[c] * wmx_pow2(wmx_unit_exp(c));
   return s;
 }
+
+// ---- what a thread carries for the (well, column) it is summing -----------------------------------
+// The sums of the two exponent classes seen last (a column's values rarely straddle more), held as
+// float64: at most 2^16 values of one class are integers below 2^47 in units of the class -- exact.
+// They become integer multiples of the class unit when they leave through `sink(class, units)`.
+struct WmxSlots {
+  double a0 = 0.0, a1 = 0.0;
+  int c0 = -1, c1 = -1, nan = 0, inf = 0;
+};
+
+WMX_HD int wmx_class(uint32_t bits) { return (int)((bits >> 26) & 31u); }
+
+// a class sum held as float64 -> its (exact) integer multiple of the class unit
+WMX_HD unsigned long long wmx_units(double a, int c) {
+  return (unsigned long long)(long long)(a * wmx_pow2(-wmx_unit_exp(c)));
+}
+
+// Hot path, branch-free (the lanes of a warp are different columns in different classes: an if-chain
+// would run every arm for every warp): x = the value widened; it is added to the slot whose class it
+// has, zero to the other.  Returns true when NO slot took it: wmx_slow must see the value.
+WMX_HD bool wmx_fast(WmxSlots& t, uint32_t bits, double x) {
+  const int c = wmx_class(bits);
+  const bool h0 = c == t.c0, h1 = c == t.c1;
+  t.a0 += h0 ? x : 0.0;
+  t.a1 += h1 ? x : 0.0;
+  return !(h0 || h1);
+}
+
+// Everything else: zero, NaN (skipped, counted in t.nan), +-inf (flag bits 1 / 2), the top class (never
+// held in a slot: NaN and inf share its number), a class no slot holds (the older slot leaves).  Safe to
+// call for any value, also one a slot has meanwhile been opened for.
+template <class Sink>
+WMX_HD void wmx_slow(WmxSlots& t, uint32_t bits, double x, Sink&& sink) {
+  const int c = wmx_class(bits);
+  const uint32_t absb = bits & 0x7fffffffu;
+  if (absb == 0u) return;
+  if (absb >= 0x7f800000u) {
+    if (absb > 0x7f800000u) ++t.nan;
+    else t.inf |= (bits >> 31) ? 2 : 1;
+    return;
+  }
+  if (c == t.c0) { t.a0 += x; return; }
+  if (c == t.c1) { t.a1 += x; return; }
+  if (c == WMX_CLASSES - 1) { sink(c, wmx_units(x, c)); return; }
+  if (t.c1 >= 0 && t.a1 != 0.0) sink(t.c1, wmx_units(t.a1, t.c1));
+  t.c1 = t.c0; t.a1 = t.a0;
+  t.c0 = c; t.a0 = x;
+}
+
+template <class Sink>
+WMX_HD void wmx_leave(const WmxSlots& t, Sink&& sink) {
+  if (t.c0 >= 0 && t.a0 != 0.0) sink(t.c0, wmx_units(t.a0, t.c0));
+  if (t.c1 >= 0 && t.a1 != 0.0) sink(t.c1, wmx_units(t.a1, t.c1));
+}

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HDR = os.path.join(ROOT, "image_processing_suite_b200", "csrc", "wellmean_exact.cuh")
 
 SRC = r'''
+#include <string.h>
 #include "%s"
 extern "C" int split(uint32_t bits, int* cls, long long* mult) { return wmx_split(bits, cls, mult) ? 1 : 0; }
 extern "C" int unit_exp(int c) { return wmx_unit_exp(c); }
@@ -21,6 +22,21 @@ extern "C" void class_sums(const uint32_t* bits, long n, long long* acc) {
   for (long i = 0; i < n; ++i) { int c; long long m; if (wmx_split(bits[i], &c, &m)) acc[c] += m; }
 }
 extern "C" double total(const long long* acc) { return wmx_total(acc); }
+// one thread of the kernel: batches of 8 through the branch-free adds, the values no slot took seen again
+// by wmx_slow after the batch (wm_batch in wellmean.cu), the tail value by value, slots leave at the end
+extern "C" void thread_sums(const float* v, long n, long long* acc, int* nan_inf) {
+  WmxSlots t;
+  auto sink = [&](int c, unsigned long long units) { acc[c] += (long long)units; };
+  long i = 0;
+  for (; i + 8 <= n; i += 8) {
+    unsigned odd = 0u;
+    for (int j = 0; j < 8; ++j) { uint32_t b; memcpy(&b, &v[i + j], 4); odd |= wmx_fast(t, b, (double)v[i + j]) ? (1u << j) : 0u; }
+    if (odd) for (int j = 0; j < 8; ++j) if (odd & (1u << j)) { uint32_t b; memcpy(&b, &v[i + j], 4); wmx_slow(t, b, (double)v[i + j], sink); }
+  }
+  for (; i < n; ++i) { uint32_t b; memcpy(&b, &v[i], 4); if (wmx_fast(t, b, (double)v[i])) wmx_slow(t, b, (double)v[i], sink); }
+  wmx_leave(t, sink);
+  nan_inf[0] = t.nan; nan_inf[1] = t.inf;
+}
 ''' % HDR
 
 
@@ -78,3 +94,39 @@ def test_class_sums_are_exact_and_order_independent(lib):
     acc3 = (ctypes.c_longlong * 32)()
     lib.class_sums(area.view(np.uint32).ctypes.data_as(ctypes.c_void_p), ctypes.c_long(area.size), acc3)
     assert lib.total(acc3) == float(area.astype(np.float64).sum())
+
+
+@pytest.mark.parametrize("kind", ["one class", "two classes", "many classes", "specials"])
+def test_thread_slots_deliver_the_exact_class_sums(lib, kind):
+    """The per-thread part of the kernel (two float64 class slots, deferred rare path) hands exactly the
+    class sums of its values to the integer accumulators, whatever the mix of classes; NaNs are counted,
+    infinities flagged, neither reaches a sum."""
+    rng = np.random.default_rng({"one class": 3, "two classes": 4, "many classes": 5, "specials": 6}[kind])
+    n = 64
+    if kind == "one class":
+        v = rng.uniform(600.0, 900.0, n)
+    elif kind == "two classes":
+        v = rng.uniform(80.0, 900.0, n) * rng.choice([-1.0, 1.0], n)        # straddles 512 = a class boundary
+    elif kind == "many classes":
+        v = rng.normal(0.0, 1.0, n) * 10.0 ** rng.integers(-30, 30, n)
+    else:
+        v = rng.normal(0.0, 1.0, n) * 10.0 ** rng.integers(-3, 3, n)
+        v[[1, 9, 10, 33]] = np.nan
+        v[[2, 40]] = np.inf
+        v[5] = -np.inf
+        v[[0, 7, 8, 63]] = 0.0
+        v[11] = -0.0
+        v[12] = 3.0e38                                                      # the top class: never held in a slot
+        v[13] = 1.0e-42                                                     # a denormal
+    v = v.astype(np.float32)
+    for m in (n, n - 3, 5):                                                 # full batches, a tail, tail only
+        part = np.ascontiguousarray(v[:m])
+        acc = (ctypes.c_longlong * 32)()
+        flags = (ctypes.c_int * 2)()
+        lib.thread_sums(part.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(m), acc, flags)
+        finite = np.ascontiguousarray(part[np.isfinite(part)])
+        want = (ctypes.c_longlong * 32)()
+        lib.class_sums(finite.view(np.uint32).ctypes.data_as(ctypes.c_void_p), ctypes.c_long(finite.size), want)
+        assert list(acc) == list(want)
+        assert flags[0] == int(np.isnan(part).sum())
+        assert flags[1] == (1 if np.any(part == np.inf) else 0) | (2 if np.any(part == -np.inf) else 0)
