@@ -103,6 +103,13 @@ __device__ __forceinline__ void wm_batch(WmPlain& t, const double (&v)[WM_UNROLL
     else ++t.nan;
   }
 }
+// the slots of a fresh run opened from its first batch (a thread's run is 64 rows: if the first value
+// of every class went through the rare branch, most warp batches would have some lane in it)
+__device__ __forceinline__ void wm_seed(WmExact& t, const float (&v)[WM_UNROLL]) {
+#pragma unroll
+  for (int j = 0; j < WM_UNROLL; ++j) wmx_seed(t.s, __float_as_uint(v[j]));
+}
+__device__ __forceinline__ void wm_seed(WmPlain&, const double (&)[WM_UNROLL]) {}
 // one value (tails of a thread's rows, tiles that span wells)
 __device__ __forceinline__ void wm_take(WmExact& t, float v, const WmOut& o, int w, int D, int d) {
   if (wmx_fast(t.s, __float_as_uint(v), (double)v)) wmx_slow(t.s, __float_as_uint(v), (double)v, wm_sink(o, w, D, d));
@@ -146,6 +153,7 @@ __device__ __forceinline__ void wm_thread_rows(const T* __restrict__ pv, const i
       for (int j = 0; j < WM_UNROLL; ++j, p += stride) nx[j] = *p;
     }
     if (UNIFORM) {
+      if (b == 0) wm_seed(run, v);
       run.k += WM_UNROLL;
       wm_batch(run, v, out, cur, D, d);
     } else {

@@ -66,6 +66,16 @@ WMX_HD unsigned long long wmx_units(double a, int c) {
   return (unsigned long long)(long long)(a * wmx_pow2(-wmx_unit_exp(c)));
 }
 
+// Opening the slots ahead of the values: called on the first few values of a run, in order, it gives the
+// two slots the first two classes that occur (zeros and the top class never claim one), so that the
+// first values do not all pass through wmx_slow.
+WMX_HD void wmx_seed(WmxSlots& t, uint32_t bits) {
+  const int c = wmx_class(bits);
+  const bool ok = (bits & 0x7fffffffu) != 0u && c != WMX_CLASSES - 1;
+  if (ok && t.c0 < 0) t.c0 = c;
+  else if (ok && c != t.c0 && t.c1 < 0) t.c1 = c;
+}
+
 // Hot path, branch-free (the lanes of a warp are different columns in different classes: an if-chain
 // would run every arm for every warp): x = the value widened; it is added to the slot whose class it
 // has, zero to the other.  Returns true when NO slot took it: wmx_slow must see the value.

@@ -29,6 +29,7 @@ extern "C" void thread_sums(const float* v, long n, long long* acc, int* nan_inf
   auto sink = [&](int c, unsigned long long units) { acc[c] += (long long)units; };
   long i = 0;
   for (; i + 8 <= n; i += 8) {
+    if (i == 0) for (int j = 0; j < 8; ++j) { uint32_t b; memcpy(&b, &v[j], 4); wmx_seed(t, b); }
     unsigned odd = 0u;
     for (int j = 0; j < 8; ++j) { uint32_t b; memcpy(&b, &v[i + j], 4); odd |= wmx_fast(t, b, (double)v[i + j]) ? (1u << j) : 0u; }
     if (odd) for (int j = 0; j < 8; ++j) if (odd & (1u << j)) { uint32_t b; memcpy(&b, &v[i + j], 4); wmx_slow(t, b, (double)v[i + j], sink); }
