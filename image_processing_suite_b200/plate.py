@@ -255,7 +255,9 @@ class PlateRowExchange:
     * otherwise one fixed-size ``ncclAllGather`` per chunk (``BlockGatherer``).
 
     All ranks take the same path (agreed with one all-reduce at construction).  One rank: the rows are
-    only packed.  Nothing here synchronises with the device except ``counts()``.
+    only packed.  Nothing here synchronises with the device except ``counts()`` and ``release()``.
+    Between two plates on the same exchange every rank calls ``release()`` (or passes a barrier of its
+    own) once it has consumed the table: the tables are written by the peers.
     """
 
     def __init__(self, n_chunks, chunk_fields, n_max, channels, group=None, peer_push=True, exact_push=True,
@@ -348,6 +350,15 @@ class PlateRowExchange:
                     self.gatherer.gather(self.chunk_counts)
         torch.cuda.current_stream(self.dev).wait_stream(self.stream)
         return self.blocks()
+
+    def release(self):
+        """This rank is done reading the gathered table.  Returns when every rank is: only then may the
+        next plate's ``submit`` calls begin -- a push of the next plate stores into the peers' tables, and a
+        peer that is still summing or copying the previous plate would see the new rows.  (One barrier per
+        plate, outside the plate's own stream of work; bench.py has its own barrier at that point.)"""
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
 
     def blocks(self):
         return self.table.view(self.n_chunks * self.world, self.block_rows, self.D)

@@ -223,6 +223,7 @@ def _exchange_worker(rank, world, port, tmp):
                 np.testing.assert_array_equal(cc, counts)
                 valid = [blocks[b, 1:1 + int(c)].cpu() for b, c in enumerate(counts.reshape(-1))]
                 results[(str(mode), rep)] = {"rows": valid, "mean": mean.cpu(), "count": count.cpu()}
+                ex.release()                                    # the peers write this table: all ranks done before the next plate
             ex.close()
         torch.save(results, os.path.join(tmp, f"x{rank}.pt"))
     finally:
