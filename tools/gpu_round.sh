@@ -7,6 +7,8 @@
 #   aux              secondary kernels (illumination, Lanczos, K1 bin sweep, K1 TMA variant)
 #   cosine [n] [d]   tensor-core cosine kernel on an n x d group
 #   tiff             device TIFF-LZW codec: parity tests, then throughput beside Pillow
+#   wellagg [N] [K]  the tail of the plate step on one GPU: well sums over the table an N-rank K-step run gathers
+#   files [sites]    the file-level drop-in scripts (TIFF files in -> TIFF / CSV files out) with stage times
 # Everything lands in gpurun_out/; copy what should be judged into profiles/.
 set -u
 mkdir -p gpurun_out
@@ -53,6 +55,13 @@ case "$what" in
     echo "tiff tests rc=$?"; tail -n 30 gpurun_out/tiff_tests.log
     timeout 600 python tools/bench_tiff.py > gpurun_out/bench_tiff.jsonl 2> gpurun_out/bench_tiff.err; echo "bench rc=$?"
     cat gpurun_out/bench_tiff.jsonl; tail -n 5 gpurun_out/bench_tiff.err
+    ;;
+  wellagg)
+    python tools/bench_wellagg.py --world "${2:-8}" --steps "${3:-20}" --chunks 20 | tee gpurun_out/wellagg.json
+    ;;
+  files)
+    IPS_IO_TRACE=1 python tools/bench_files.py --sites "${2:-256}" --distinct 4 --cpu-sites 1 > gpurun_out/files.json 2> gpurun_out/files.err
+    echo "files rc=$?"; cat gpurun_out/files.json; grep -i "stages" gpurun_out/files.err | tail -n 4
     ;;
   *) echo "unknown: $what"; exit 2 ;;
 esac
