@@ -44,3 +44,28 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == os.cpu_count()
     assert d["e2e"] == {"value": d["value"], "unit": "fields/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+def test_committed_bench_lines_carry_the_contract():
+    """The bench lines kept under profiles/ (written by bench.py on a B200) carry every key the measurement
+    contract names, and their numbers are consistent with each other."""
+    for name in ("r2f_bench.json", "r2g_bench_20steps_final.json"):
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            d = json.loads(f.read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+            assert k in d, (name, k)
+        assert d["unit"] == "fields/s" and d["scaling"] == "weak" and d["vs_baseline"] is None and d["gpu_launches"] > 0
+        assert "workload" in d["config"] and "model" not in d["config"]
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert 0.5 < r["frac"] < 1.0 and r["traffic"] is not None
+        # value = fields of all steps / the timed region
+        fields = d["steps"] * d["config"]["fields_per_step"] * d["n_gpus"]
+        assert abs(d["value"] - fields / (d["ms_per_step"] * d["steps"] * 1e-3)) < 1e-6 * d["value"]
+        e = d["e2e"]
+        assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+        c = d["cpu_baseline"]
+        assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+        assert d["aggregation"]["check"] == "ok"
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
