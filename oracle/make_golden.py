@@ -241,6 +241,46 @@ def tiff_golden():
     np.savez_compressed(os.path.join(OUT, "tiff_lzw.npz"), **cases)
 
 
+class _Body:
+    def __init__(self, b):
+        self.b = b
+
+    def read(self):
+        return self.b
+
+
+class _MemoryS3:
+    """The slice of the boto3 S3 client the tabular scripts use, over a dict {(bucket, key): bytes}."""
+
+    def __init__(self, store):
+        self.store = store
+
+    def get_object(self, Bucket, Key):
+        return {"Body": _Body(self.store[(Bucket, Key)])}
+
+    def put_object(self, Bucket, Key, Body):
+        self.store[(Bucket, Key)] = Body.encode() if isinstance(Body, str) else Body
+
+    def list_objects_v2(self, Bucket, Prefix, Delimiter=None):
+        keys = sorted(k for b, k in self.store if b == Bucket and k.startswith(Prefix)
+                      and (Delimiter is None or Delimiter not in k[len(Prefix):]))
+        return {"Contents": [{"Key": k} for k in keys]}
+
+
+def _load_with_stubs(filename, modname, stubs):
+    """Import a reference script with ``stubs`` ({module name: module}) in sys.modules for the duration."""
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        return _load(filename, modname)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
 def well_agg_golden():
     """The well-level aggregation of Normalize_CP_ami.concatenate_csv_from_s3 (:29-151) run by the
     REFERENCE's own code on small tables: boto3 is an in-memory bucket, pycytominer (absent) is stubbed
@@ -251,23 +291,8 @@ def well_agg_golden():
     import pandas as pd
     bucket = {}
     seen = {}
-
-    class Body:
-        def __init__(self, b):
-            self.b = b
-
-        def read(self):
-            return self.b
-
-    class S3:
-        def get_object(self, Bucket, Key):
-            return {"Body": Body(bucket[(Bucket, Key)])}
-
-        def put_object(self, Bucket, Key, Body):
-            bucket[(Bucket, Key)] = Body.encode() if isinstance(Body, str) else Body
-
     boto3 = types.ModuleType("boto3")
-    boto3.client = lambda *a, **k: S3()
+    boto3.client = lambda *a, **k: _MemoryS3(bucket)
     botocore = types.ModuleType("botocore")
     config = types.ModuleType("botocore.config")
     config.Config = lambda **k: None
@@ -283,16 +308,8 @@ def well_agg_golden():
         return profiles.copy()
 
     pyc.annotate, pyc.normalize = annotate, normalize
-    saved = {k: sys.modules.get(k) for k in ("boto3", "botocore", "botocore.config", "pycytominer")}
-    sys.modules.update({"boto3": boto3, "botocore": botocore, "botocore.config": config, "pycytominer": pyc})
-    try:
-        ref = _load("Normalize_CP_ami.py", "ref_normalize")
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
+    ref = _load_with_stubs("Normalize_CP_ami.py", "ref_normalize",
+                           {"boto3": boto3, "botocore": botocore, "botocore.config": config, "pycytominer": pyc})
     rng = np.random.default_rng(20261019)
     wells = [f"{r}{c:02d}" for r in "ABC" for c in range(1, 6)]
     rows_img, tabs = [], {"Nuclei": [], "Cells": [], "Cytoplasm": []}
@@ -341,44 +358,15 @@ def cosine_script_golden():
     sigmoid (:26-27, :117-118), the fillna / grouping rules and the per-group mean cosine (:131-156)."""
     import pandas as pd
     bucket = {}
-
-    class Body:
-        def __init__(self, b):
-            self.b = b
-
-        def read(self):
-            return self.b
-
-    class S3:
-        def get_object(self, Bucket, Key):
-            return {"Body": Body(bucket[(Bucket, Key)])}
-
-        def put_object(self, Bucket, Key, Body):
-            bucket[(Bucket, Key)] = Body.encode() if isinstance(Body, str) else Body
-
-        def list_objects_v2(self, Bucket, Prefix, Delimiter=None):
-            keys = sorted(k for b, k in bucket if b == Bucket and k.startswith(Prefix)
-                          and (Delimiter is None or Delimiter not in k[len(Prefix):]))
-            return {"Contents": [{"Key": k} for k in keys]}
-
     boto3 = types.ModuleType("boto3")
-    boto3.client = lambda *a, **k: S3()
+    boto3.client = lambda *a, **k: _MemoryS3(bucket)
     pyc = types.ModuleType("pycytominer")
 
     def feature_select(profiles, features, samples, operation, output_file, output_type, na_cutoff=None, corr_threshold=None):
         profiles.to_csv(output_file, index=False)
 
     pyc.feature_select = feature_select
-    saved = {k: sys.modules.get(k) for k in ("boto3", "pycytominer")}
-    sys.modules.update({"boto3": boto3, "pycytominer": pyc})
-    try:
-        ref = _load("Feature_select_cosine_ami.py", "ref_cosine_script")
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
+    ref = _load_with_stubs("Feature_select_cosine_ami.py", "ref_cosine_script", {"boto3": boto3, "pycytominer": pyc})
     rng = np.random.default_rng(20261020)
     cases = {}
     for plate in ("P1", "P2"):
@@ -419,23 +407,8 @@ def pycyto_golden():
     reference's ``dtype == 'object'`` test (:65) does not catch ``str`` columns under current pandas.)"""
     import pandas as pd
     bucket = {}
-
-    class Body:
-        def __init__(self, b):
-            self.b = b
-
-        def read(self):
-            return self.b
-
-    class S3:
-        def get_object(self, Bucket, Key):
-            return {"Body": Body(bucket[(Bucket, Key)])}
-
-        def put_object(self, Bucket, Key, Body):
-            bucket[(Bucket, Key)] = Body.encode() if isinstance(Body, str) else Body
-
     boto3 = types.ModuleType("boto3")
-    boto3.client = lambda *a, **k: S3()
+    boto3.client = lambda *a, **k: _MemoryS3(bucket)
     pyc = types.ModuleType("pycytominer")
     pyc.annotate = lambda *a, **k: None
     pyc.normalize = lambda profiles, features, samples, method: profiles.copy()
@@ -444,16 +417,7 @@ def pycyto_golden():
         profiles.to_csv(output_file, index=False)
 
     pyc.feature_select = feature_select
-    saved = {k: sys.modules.get(k) for k in ("boto3", "pycytominer")}
-    sys.modules.update({"boto3": boto3, "pycytominer": pyc})
-    try:
-        ref = _load("Pycyto_pertime.py", "ref_pycyto")
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
+    ref = _load_with_stubs("Pycyto_pertime.py", "ref_pycyto", {"boto3": boto3, "pycytominer": pyc})
     rng = np.random.default_rng(20261021)
     img_rows, tabs = [], {"Nuclei": [], "Cells": [], "Cytoplasm": []}
     n = 0
