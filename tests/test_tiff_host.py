@@ -174,6 +174,9 @@ def test_product_parser_matches_oracle_and_rejects_other_layouts():
         assert (a["width"], a["height"], a["compression"], a["predictor"], a["rows_per_strip"]) == \
                (b["width"], b["height"], b["compression"], b["predictor"], b["rps"])
         assert a["offsets"] == b["offsets"] and a["counts"] == b["counts"]
+        # the same tables as int64 arrays (what decode_staged takes, built on the reader threads)
+        assert a["offsets_np"].dtype == np.int64 and a["offsets_np"].tolist() == a["offsets"]
+        assert a["counts_np"].dtype == np.int64 and a["counts_np"].tolist() == a["counts"]
     for kw in ({"compression": "tiff_adobe_deflate"},):
         buf = io.BytesIO()
         Image.fromarray(img).save(buf, format="tiff", **kw)
